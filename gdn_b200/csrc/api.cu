@@ -1,0 +1,312 @@
+// api.cu -- extern "C" entry points of libgdn_b200.so (see include/gdn_b200.h).
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+#include "launchers.h"
+
+namespace gdn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e > 0 ? (int)e : 1;
+}
+
+int num_sms() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+int make_shape(const gdn_dims* d, Shape* s, bool need_dwide) {
+    GDN_CHECK_ARG(d != nullptr, "dims is NULL");
+    GDN_CHECK_ARG(d->B >= 1 && d->N >= 1, "B=%d N=%d must be positive", d->B, d->N);
+    GDN_CHECK_ARG(d->W >= 1 && d->W <= 32, "slide_win W=%d unsupported (1..32)", d->W);
+    GDN_CHECK_ARG(d->K >= 1 && d->K <= d->N, "topk K=%d must be in 1..N=%d", d->K, d->N);
+    GDN_CHECK_ARG(d->D >= 1, "dim D=%d must be positive", d->D);
+    if (need_dwide)
+        GDN_CHECK_ARG(d->D % 32 == 0 && d->D <= 256 && (d->D == 32 || d->D == 64 || d->D == 128 || d->D == 256),
+                      "dim D=%d unsupported by the fused kernels (32, 64, 128, 256)", d->D);
+    s->B = d->B; s->N = d->N; s->W = d->W; s->D = d->D; s->K = d->K;
+    s->Kp = d->K + 1;
+    s->Bs = round_up32(d->B);
+    s->n = (long long)d->B * d->N;
+    s->WP = d->W <= 8 ? 8 : (d->W <= 16 ? 16 : 32);
+    s->DPL = d->D / 32;
+    // sensor-major passes: tasks = N * S; aim for >= 8 tasks per resident warp slot
+    const long long want = (long long)num_sms() * 8 * 4;
+    int S = (int)((want + d->N - 1) / d->N);
+    if (S < 1) S = 1;
+    if (S > d->B) S = d->B;
+    int rps = (d->B + S - 1) / S;
+    S = (d->B + rps - 1) / rps;
+    s->S = S;
+    s->rows_per_split = rps;
+    return 0;
+}
+
+static size_t take(size_t* off, size_t bytes) {
+    const size_t at = *off;
+    *off = align_up(at + bytes, 256);
+    return at;
+}
+
+CtxLayout ctx_layout(const Shape& s, bool fused) {
+    CtxLayout L;
+    size_t off = 0;
+    const size_t nb = (size_t)s.N * s.Bs * sizeof(float);
+    L.xT = take(&off, nb * s.W);
+    L.siT = take(&off, nb);
+    L.sjT = take(&off, nb);
+    L.mT = take(&off, nb);
+    L.linvT = take(&off, nb);
+    L.A = take(&off, (size_t)s.n * s.W * sizeof(float));
+    L.uv = take(&off, 64 * sizeof(float));
+    L.ev = take(&off, (size_t)2 * s.N * sizeof(float));
+    L.bn = take(&off, fused ? (size_t)8 * s.D * sizeof(float) : 0);
+    L.bits = take(&off, fused ? (size_t)s.n * s.DPL * sizeof(uint32_t) : 0);
+    L.flags = take(&off, 4 * sizeof(int));
+    L.total = off;
+    return L;
+}
+
+WsLayout ws_layout(const Shape& s, bool fused) {
+    WsLayout L;
+    size_t off = 0;
+    L.gA = take(&off, (size_t)s.n * s.W * sizeof(float));
+    const size_t nb = (size_t)s.N * s.Bs * sizeof(float);
+    L.gsiT = take(&off, nb);
+    L.gsjT = take(&off, nb);
+    size_t rec = (size_t)s.D * s.W + s.D;
+    if ((size_t)3 * s.D + 32 > rec) rec = (size_t)3 * s.D + 32;
+    if ((size_t)s.W * s.W + s.W > rec) rec = (size_t)s.W * s.W + s.W;
+    L.part_bytes = (size_t)2 * num_sms() * rec * sizeof(double);
+    L.part = take(&off, L.part_bytes);
+    L.gV = take(&off, (fused && s.S > 1) ? (size_t)s.S * s.N * s.D * sizeof(float) : 0);
+    // small: c2[2D] c1[2D] gev[2N] part_u[2*sms*64] part_e[2*sms*2D]   (floats)
+    L.small = take(&off, ((size_t)4 * s.D + 2 * s.N + (size_t)2 * num_sms() * (64 + 2 * s.D)) * sizeof(float));
+    L.total = off;
+    return L;
+}
+
+struct Small {
+    float *c2, *c1, *gev, *part_u, *part_e;
+};
+static Small small_ptrs(const Shape& s, char* ws, const WsLayout& L) {
+    Small m;
+    float* p = (float*)(ws + L.small);
+    m.c2 = p; p += 2 * s.D;
+    m.c1 = p; p += 2 * s.D;
+    m.gev = p; p += 2 * s.N;
+    m.part_u = p; p += (size_t)2 * num_sms() * 64;
+    m.part_e = p;
+    return m;
+}
+
+static HeadArgs head_args(const Shape& s, const char* ctx, const CtxLayout& L, const float* V,
+                          const gdn_layer_params* p, const gdn_head_params* h, const gdn_dropout* dp, int training) {
+    HeadArgs a;
+    a.A = (const float*)(ctx + L.A);
+    a.V = V;
+    a.Wl = p->lin_weight;
+    a.bnc = (const float*)(ctx + L.bn);
+    a.g1 = h->bn1.weight; a.be1 = h->bn1.bias; a.g2 = h->bn2.weight; a.be2 = h->bn2.bias;
+    a.wo = h->out_w; a.bo = h->out_b;
+    a.B = s.B; a.N = s.N; a.W = s.W; a.D = s.D; a.S = s.S; a.rps = s.rows_per_split;
+    a.mask = dp ? dp->mask : nullptr;
+    a.bits = (uint32_t*)(const_cast<char*>(ctx) + L.bits);
+    a.seed = dp ? dp->seed : 0ull;
+    a.offset = dp ? dp->offset : 0ull;
+    a.p_drop = dp ? dp->p : 0.f;
+    a.scale = (dp && dp->p > 0.f && dp->p < 1.f) ? 1.f / (1.f - dp->p) : 1.f;
+    a.training = training;
+    return a;
+}
+
+}  // namespace gdn
+
+using namespace gdn;
+
+extern "C" {
+
+int gdn_version(void) { return GDN_B200_VERSION; }
+const char* gdn_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------- graph
+size_t gdn_graph_build_ws_bytes(int N, int D, int K) { return graph_build_ws_bytes(N, D, K); }
+
+int gdn_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, size_t ws_bytes,
+                    int use_tensor_cores, void* stream) {
+    GDN_CHECK_ARG(V != nullptr, "V is NULL");
+    GDN_CHECK_ARG(N >= 1 && D >= 1 && K >= 1 && K <= N, "graph_build: bad shape N=%d D=%d K=%d", N, D, K);
+    return launch_graph_build(V, N, D, K, idx, nbr, ws, ws_bytes, use_tensor_cores, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------- GraphLayer (shared graph)
+size_t gdn_graphlayer_ctx_bytes(const gdn_dims* d) {
+    Shape s;
+    if (make_shape(d, &s, true)) return 0;
+    return ctx_layout(s, false).total;
+}
+size_t gdn_graphlayer_ws_bytes(const gdn_dims* d) {
+    Shape s;
+    if (make_shape(d, &s, true)) return 0;
+    return ws_layout(s, false).total;
+}
+
+int gdn_graphlayer_fwd(const gdn_dims* d, const float* x, const float* V, const int32_t* nbr,
+                       const gdn_layer_params* p, float* out, float* alpha, void* ctx_, void* ws, size_t ws_bytes,
+                       void* stream) {
+    Shape s;
+    if (int rc = make_shape(d, &s, true)) return rc;
+    GDN_CHECK_ARG(x && V && nbr && p && out && ctx_, "graphlayer_fwd: NULL argument");
+    const CtxLayout L = ctx_layout(s, false);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ctx = (char*)ctx_;
+    (void)ws; (void)ws_bytes;
+    if (int rc = launch_prep(s, x, V, p, ctx, L, st)) return rc;
+    if (int rc = launch_attn_fwd(s, nbr, ctx, L, alpha, st)) return rc;
+    return launch_lin_fwd(s, (const float*)(ctx + L.A), p, out, st);
+}
+
+int gdn_graphlayer_bwd(const gdn_dims* d, const float* g_out, const float* V, const int32_t* nbr,
+                       const gdn_layer_params* p, const void* ctx_, gdn_layer_grads* g, void* ws_, size_t ws_bytes,
+                       void* stream) {
+    Shape s;
+    if (int rc = make_shape(d, &s, true)) return rc;
+    GDN_CHECK_ARG(g_out && V && nbr && p && ctx_ && g && ws_, "graphlayer_bwd: NULL argument");
+    GDN_CHECK_ARG(g->lin_weight && g->att_i && g->att_j && g->att_em_i && g->att_em_j && g->embedding,
+                  "graphlayer_bwd: NULL gradient buffer");
+    const CtxLayout L = ctx_layout(s, false);
+    const WsLayout WL = ws_layout(s, false);
+    GDN_CHECK_ARG(ws_bytes >= WL.total, "graphlayer_bwd: workspace too small (%zu < %zu)", ws_bytes, WL.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* ctx = (const char*)ctx_;
+    char* ws = (char*)ws_;
+    const Small sm = small_ptrs(s, ws, WL);
+    float* gA = (float*)(ws + WL.gA);
+    double* part = (double*)(ws + WL.part);
+    int nrec = 0, nrec_u = 0, nrec_e = 0;
+    if (int rc = launch_lin_bwd(s, g_out, (const float*)(ctx + L.A), p, gA, part, &nrec, st)) return rc;
+    if (int rc = launch_attn_bwd(s, nbr, ctx, L, gA, (float*)(ws + WL.gsiT), (float*)(ws + WL.gsjT), sm.gev,
+                                 sm.part_u, &nrec_u, st)) return rc;
+    if (int rc = launch_fin_layer(s, part, nrec, sm.part_u, nrec_u, p, g, st)) return rc;
+    if (int rc = launch_embed_grads(s, V, sm.gev, p, 0, g->embedding, sm.part_e, &nrec_e, st)) return rc;
+    return launch_fin_embed(s, sm.part_e, nrec_e, g, st);
+}
+
+// ------------------------------------------------------------------------------- fused GDN
+size_t gdn_fused_ctx_bytes(const gdn_dims* d) {
+    Shape s;
+    if (make_shape(d, &s, true)) return 0;
+    return ctx_layout(s, true).total;
+}
+size_t gdn_fused_ws_bytes(const gdn_dims* d) {
+    Shape s;
+    if (make_shape(d, &s, true)) return 0;
+    return ws_layout(s, true).total;
+}
+
+int gdn_fused_fwd(const gdn_dims* d, const float* x, const float* V, const int32_t* nbr, const gdn_layer_params* p,
+                  const gdn_head_params* h, const gdn_dropout* dp, int training, float* pred, void* ctx_, void* ws_,
+                  size_t ws_bytes, void* stream) {
+    Shape s;
+    if (int rc = make_shape(d, &s, true)) return rc;
+    GDN_CHECK_ARG(x && V && nbr && p && h && pred && ctx_ && ws_, "fused_fwd: NULL argument");
+    GDN_CHECK_ARG(p->bias != nullptr, "fused_fwd: gnn.bias must be given (pass zeros for bias=False)");
+    GDN_CHECK_ARG(!training || s.n > 1, "fused_fwd: BatchNorm needs more than one row in training mode");
+    GDN_CHECK_ARG(!dp || (dp->p >= 0.f && dp->p < 1.f), "fused_fwd: dropout p must be in [0, 1)");
+    const CtxLayout L = ctx_layout(s, true);
+    const WsLayout WL = ws_layout(s, true);
+    GDN_CHECK_ARG(ws_bytes >= WL.total, "fused_fwd: workspace too small (%zu < %zu)", ws_bytes, WL.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ctx = (char*)ctx_;
+    char* ws = (char*)ws_;
+    float* bnc = (float*)(ctx + L.bn);
+    double* part = (double*)(ws + WL.part);
+    if (int rc = launch_prep(s, x, V, p, ctx, L, st)) return rc;
+    if (int rc = launch_attn_fwd(s, nbr, ctx, L, nullptr, st)) return rc;
+    const HeadArgs ha = head_args(s, ctx, L, V, p, h, dp, training);
+    if (training) {
+        int nrec = 0;
+        if (int rc = launch_moments(s, ha.A, part, &nrec, st)) return rc;
+        if (int rc = launch_fin_bn1(s, part, nrec, p, bnc, &h->bn1, st)) return rc;
+        if (int rc = launch_fwd_stats2(s, ha, part, &h->bn2, bnc, st)) return rc;
+    } else {
+        if (int rc = launch_fin_bn_eval(s, p, h, bnc, st)) return rc;
+    }
+    return launch_fwd_out(s, ha, pred, st);
+}
+
+int gdn_fused_bwd(const gdn_dims* d, const float* g_pred, const float* V, const int32_t* nbr,
+                  const gdn_layer_params* p, const gdn_head_params* h, const gdn_dropout* dp, const void* ctx_,
+                  gdn_layer_grads* g, gdn_head_grads* gh, void* ws_, size_t ws_bytes, void* stream) {
+    Shape s;
+    if (int rc = make_shape(d, &s, true)) return rc;
+    GDN_CHECK_ARG(g_pred && V && nbr && p && h && ctx_ && g && gh && ws_, "fused_bwd: NULL argument");
+    GDN_CHECK_ARG(g->lin_weight && g->att_i && g->att_j && g->att_em_i && g->att_em_j && g->bias && g->embedding,
+                  "fused_bwd: NULL layer gradient buffer");
+    GDN_CHECK_ARG(gh->bn1_weight && gh->bn1_bias && gh->bn2_weight && gh->bn2_bias && gh->out_w && gh->out_b,
+                  "fused_bwd: NULL head gradient buffer");
+    const CtxLayout L = ctx_layout(s, true);
+    const WsLayout WL = ws_layout(s, true);
+    GDN_CHECK_ARG(ws_bytes >= WL.total, "fused_bwd: workspace too small (%zu < %zu)", ws_bytes, WL.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* ctx = (const char*)ctx_;
+    char* ws = (char*)ws_;
+    const Small sm = small_ptrs(s, ws, WL);
+    double* part = (double*)(ws + WL.part);
+    const HeadArgs ha = head_args(s, ctx, L, V, p, h, dp, /*training=*/1);
+    BwdArgs ba;
+    ba.gpred = g_pred;
+    ba.c2 = sm.c2;
+    ba.c1 = sm.c1;
+    ba.gV = s.S > 1 ? (float*)(ws + WL.gV) : g->embedding;
+    ba.gA = (float*)(ws + WL.gA);
+    int nrec = 0, nrec_u = 0, nrec_e = 0;
+    if (int rc = launch_bwd1(s, ha, ba, part, gh, sm.c2, st)) return rc;
+    if (int rc = launch_bwd2(s, ha, ba, part, gh, sm.c1, g->embedding, st)) return rc;
+    if (int rc = launch_bwd3(s, ha, ba, part, &nrec, st)) return rc;
+    if (int rc = launch_attn_bwd(s, nbr, ctx, L, ba.gA, (float*)(ws + WL.gsiT), (float*)(ws + WL.gsjT), sm.gev,
+                                 sm.part_u, &nrec_u, st)) return rc;
+    if (int rc = launch_fin_layer(s, part, nrec, sm.part_u, nrec_u, p, g, st)) return rc;
+    if (int rc = launch_embed_grads(s, V, sm.gev, p, 1, g->embedding, sm.part_e, &nrec_e, st)) return rc;
+    return launch_fin_embed(s, sm.part_e, nrec_e, g, st);
+}
+
+int gdn_ctx_alpha(const gdn_dims* d, const int32_t* nbr, const void* ctx_, float* alpha, void* stream) {
+    Shape s;
+    if (int rc = make_shape(d, &s, false)) return rc;
+    GDN_CHECK_ARG(nbr && ctx_ && alpha, "ctx_alpha: NULL argument");
+    // the attention part of the ctx layout does not depend on the fused flag
+    const CtxLayout L = ctx_layout(s, false);
+    return launch_attn_alpha(s, nbr, (const char*)ctx_, L, alpha, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------- scoring
+size_t gdn_score_ws_bytes(int T, int N) { return score_ws_bytes(T, N); }
+
+int gdn_score(const float* pred, const float* gt, int T, int N, double* scores, double* top1, double* stats,
+              void* ws, size_t ws_bytes, void* stream) {
+    GDN_CHECK_ARG(pred && gt, "score: NULL input");
+    GDN_CHECK_ARG(T >= 1 && N >= 1, "score: bad shape T=%d N=%d", T, N);
+    GDN_CHECK_ARG(ws != nullptr && ws_bytes >= score_ws_bytes(T, N), "score: workspace too small");
+    return launch_score(pred, gt, T, N, scores, top1, stats, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

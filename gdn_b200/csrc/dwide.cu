@@ -1,0 +1,993 @@
+// dwide.cu -- the D-wide part of the path: lin transform (W -> D), BatchNorm + ReLU,
+// (x) embedding, BatchNorm + ReLU, Dropout, Linear(D, 1), and its backward.
+//
+// Replaces models/graph_layer.py:56,71-74 (lin / head-mean / bias, applied after the
+// aggregation because lin has no bias), models/GDN.py:77-79 (GNNLayer BN+ReLU) and
+// models/GDN.py:171-187 (head), plus autograd of all of it (SURVEY.md section 8 rows
+// a3, a5, a6, a7).  Nothing D-wide is ever written to HBM in the fused path: every pass
+// recomputes Z = Wl.A from the W-wide aggregate A (16x fewer bytes than Z at W=16, D=128),
+// and the BatchNorm batch statistics -- which force grid-wide reductions -- are obtained
+//   BN1: from the first and second moments of A (Z is affine in A, so its per-channel
+//        mean/variance follow from mean(A) and cov(A): W + W^2 numbers),
+//   BN2: from one recompute pass.
+//
+// Thread mapping: lane <-> DPL = D/32 consecutive channels; a warp walks rows.  The fused
+// passes are sensor-major (a warp owns sensor i and a range of windows b), so V[i,:] stays
+// in registers and the embedding gradient needs no atomics.
+#include "common.cuh"
+#include "launchers.h"
+
+namespace gdn {
+
+// ---------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------
+template <int DPL, int WP>
+__device__ __forceinline__ void load_wl(const float* __restrict__ Wl, int W, int lane, float (&wl)[DPL][WP]) {
+#pragma unroll
+    for (int j = 0; j < DPL; ++j)
+#pragma unroll
+        for (int w = 0; w < WP; ++w) wl[j][w] = (w < W) ? Wl[(size_t)(lane * DPL + j) * W + w] : 0.f;
+}
+
+template <int WP>
+__device__ __forceinline__ void load_arow(const float* __restrict__ row, int W, float (&a)[WP]) {
+    if ((W & 3) == 0) {
+#pragma unroll
+        for (int w = 0; w < WP; w += 4) {
+            if (w < W) {
+                const float4 v = *reinterpret_cast<const float4*>(row + w);
+                a[w] = v.x; a[w + 1] = v.y; a[w + 2] = v.z; a[w + 3] = v.w;
+            } else {
+                a[w] = a[w + 1] = a[w + 2] = a[w + 3] = 0.f;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < WP; ++w) a[w] = (w < W) ? row[w] : 0.f;
+    }
+}
+
+template <int DPL>
+__device__ __forceinline__ void load_chan(const float* __restrict__ p, int lane, float (&v)[DPL]) {
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) v[j] = p[lane * DPL + j];
+}
+
+template <int DPL>
+__device__ __forceinline__ void store_chan(float* __restrict__ p, int lane, const float (&v)[DPL]) {
+    if (DPL == 4) {
+        *reinterpret_cast<float4*>(p + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (DPL == 2) {
+        *reinterpret_cast<float2*>(p + lane * 2) = make_float2(v[0], v[1]);
+    } else if (DPL == 8) {
+        *reinterpret_cast<float4*>(p + lane * 8) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + lane * 8 + 4) = make_float4(v[4 % DPL], v[5 % DPL], v[6 % DPL], v[7 % DPL]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) p[lane * DPL + j] = v[j];
+    }
+}
+
+template <int DPL>
+__device__ __forceinline__ void load_chan_vec(const float* __restrict__ p, int lane, float (&v)[DPL]) {
+    if (DPL == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p + lane * 4);
+        v[0] = t.x; v[1 % DPL] = t.y; v[2 % DPL] = t.z; v[3 % DPL] = t.w;
+    } else if (DPL == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(p + lane * 2);
+        v[0] = t.x; v[1 % DPL] = t.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) v[j] = p[lane * DPL + j];
+    }
+}
+
+// sum_{lanes} v[w] for every w; returns the total of index *w_out on this lane.
+// Butterfly reduce-scatter: log2(WP) halving steps, then plain xor-sums over the rest.
+template <int WP>
+__device__ __forceinline__ float reduce_scatter(float (&v)[WP], int lane, int* w_out) {
+    int o = 16, widx = 0;
+#pragma unroll
+    for (int cnt = WP / 2; cnt >= 1; cnt >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int t = 0; t < cnt; ++t) {
+            const float send = up ? v[t] : v[t + cnt];
+            const float keep = up ? v[t + cnt] : v[t];
+            v[t] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+        if (up) widx += cnt;
+        o >>= 1;
+    }
+    float r = v[0];
+    for (; o >= 1; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    *w_out = widx;
+    return r;
+}
+
+// per-CTA reduction of per-lane channel accumulators over the CTA's warps -> part[] (double)
+// vals[q] (q < NV) is the accumulator of channel lane*DPL + (q % DPL), quantity q / DPL.
+// Written as part[(q / DPL) * D + lane*DPL + q % DPL].
+template <int NV, int DPL>
+__device__ __forceinline__ void cta_reduce_channels(const double (&vals)[NV], int D, double* __restrict__ part,
+                                                    double* smem /* [warps][NV][32] */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) smem[((size_t)wid * NV + q) * 32 + lane] = vals[q];
+    __syncthreads();
+    for (int e = threadIdx.x; e < NV * 32; e += blockDim.x) {
+        const int q = e >> 5, l = e & 31;
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += smem[((size_t)w * NV + q) * 32 + l];
+        part[(size_t)(q / DPL) * D + l * DPL + (q % DPL)] = s;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// module boundary: out[r,:] = Wl.A[r,:] + bias            (models/graph_layer.py:56,71-74)
+// ---------------------------------------------------------------------------------------
+template <int DPL, int WP>
+__global__ void __launch_bounds__(256)
+k_lin_fwd(const float* __restrict__ A, const float* __restrict__ Wl, const float* __restrict__ bias,
+          long long n, int W, int D, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float wl[DPL][WP], bs[DPL];
+    load_wl<DPL, WP>(Wl, W, lane, wl);
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) bs[j] = bias ? bias[lane * DPL + j] : 0.f;
+#pragma unroll 2
+    for (long long r = warp; r < n; r += nwarps) {
+        float a[WP], z[DPL];
+        load_arow<WP>(A + (size_t)r * W, W, a);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < WP; ++w) acc = fmaf(wl[j][w], a[w], acc);
+            z[j] = acc + bs[j];
+        }
+        store_chan<DPL>(out + (size_t)r * D, lane, z);
+    }
+}
+
+// g_out -> g_A[r,w] = sum_d g_out[r,d] Wl[d,w];  partial g_Wl[d,w] += g_out[r,d] A[r,w];
+// partial g_bias[d] += g_out[r,d].   part record: [D*W + D] doubles.
+template <int DPL, int WP>
+__global__ void __launch_bounds__(256)
+k_lin_bwd(const float* __restrict__ gout, const float* __restrict__ A, const float* __restrict__ Wl,
+          long long n, int W, int D, float* __restrict__ gA, double* __restrict__ part) {
+    __shared__ float red[8][33][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float wl[DPL][WP], gwl[DPL][WP], gb[DPL];
+    load_wl<DPL, WP>(Wl, W, lane, wl);
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+        gb[j] = 0.f;
+#pragma unroll
+        for (int w = 0; w < WP; ++w) gwl[j][w] = 0.f;
+    }
+    for (long long r = warp; r < n; r += nwarps) {
+        float a[WP], go[DPL], pw[WP];
+        load_arow<WP>(A + (size_t)r * W, W, a);
+        load_chan_vec<DPL>(gout + (size_t)r * D, lane, go);
+#pragma unroll
+        for (int w = 0; w < WP; ++w) pw[w] = 0.f;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            gb[j] += go[j];
+#pragma unroll
+            for (int w = 0; w < WP; ++w) {
+                pw[w] = fmaf(go[j], wl[j][w], pw[w]);
+                gwl[j][w] = fmaf(go[j], a[w], gwl[j][w]);
+            }
+        }
+        int widx;
+        const float tot = reduce_scatter<WP>(pw, lane, &widx);
+        if ((lane & ((32 / WP) - 1)) == 0 && widx < W) gA[(size_t)r * W + widx] = tot;
+    }
+    double* prec = part + (size_t)blockIdx.x * ((size_t)D * W + D);
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+#pragma unroll
+        for (int w = 0; w < WP; ++w) red[wid][w][lane] = gwl[j][w];
+        red[wid][32][lane] = gb[j];
+        __syncthreads();
+        for (int e = threadIdx.x; e < 33 * 32; e += blockDim.x) {
+            const int w = e >> 5, l = e & 31;
+            if (w < W || w == 32) {
+                double s = 0.0;
+                for (int q = 0; q < 8; ++q) s += (double)red[q][w][l];
+                const int d = l * DPL + j;
+                if (w == 32) prec[(size_t)D * W + d] = s;
+                else prec[(size_t)d * W + w] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// moments of A: sum_r A[r,w], sum_r A[r,w] A[r,w']   -> part record [W*W + W] doubles
+// lane <-> w' (WP lanes), 32/WP rows in flight per warp
+// ---------------------------------------------------------------------------------------
+template <int WP>
+__global__ void __launch_bounds__(256)
+k_moments(const float* __restrict__ A, long long n, int W, double* __restrict__ part) {
+    constexpr int NW = WP == 32 ? 4 : 8;        // warps per CTA (static smem stays < 48 KB)
+    __shared__ double red[NW][WP + 1][WP];
+    constexpr int SLOTS = 32 / WP;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int slot = lane / WP, wq = lane % WP;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float acc[WP];
+#pragma unroll
+    for (int w = 0; w < WP; ++w) acc[w] = 0.f;
+    float s1 = 0.f;
+    double dacc[WP], ds1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < WP; ++w) dacc[w] = 0.0;
+    int since = 0;
+    for (long long r0 = warp * SLOTS; r0 < n; r0 += nwarps * SLOTS) {
+        const long long r = r0 + slot;
+        if (r < n) {
+            float a[WP];
+            load_arow<WP>(A + (size_t)r * W, W, a);
+            const float own = (wq < W) ? A[(size_t)r * W + wq] : 0.f;
+            s1 += own;
+#pragma unroll
+            for (int w = 0; w < WP; ++w) acc[w] = fmaf(a[w], own, acc[w]);
+        }
+        if (++since == 32) {      // flush fp32 partials into fp64 every 32 rows
+            since = 0;
+#pragma unroll
+            for (int w = 0; w < WP; ++w) { dacc[w] += (double)acc[w]; acc[w] = 0.f; }
+            ds1 += (double)s1; s1 = 0.f;
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < WP; ++w) dacc[w] += (double)acc[w];
+    ds1 += (double)s1;
+    // fold the row slots of the warp together
+#pragma unroll
+    for (int o = WP; o < 32; o <<= 1) {
+#pragma unroll
+        for (int w = 0; w < WP; ++w) dacc[w] += __shfl_xor_sync(0xffffffffu, dacc[w], o);
+        ds1 += __shfl_xor_sync(0xffffffffu, ds1, o);
+    }
+    if (slot == 0) {
+#pragma unroll
+        for (int w = 0; w < WP; ++w) red[wid][w][wq] = dacc[w];
+        red[wid][WP][wq] = ds1;
+    }
+    __syncthreads();
+    double* prec = part + (size_t)blockIdx.x * ((size_t)W * W + W);
+    for (int e = threadIdx.x; e < (WP + 1) * WP; e += blockDim.x) {
+        const int w = e / WP, q = e % WP;
+        if (q < W && (w < W || w == WP)) {
+            double s = 0.0;
+            for (int k = 0; k < NW; ++k) s += red[k][w][q];
+            if (w == WP) prec[(size_t)W * W + q] = s;
+            else prec[(size_t)w * W + q] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// fused head passes (sensor-major).  bnc = ctx.bn: 8 vectors of D floats:
+//   0 mean1  1 istd1  2 k1a (= istd1)  3 k1b (= (bias - mean1) istd1)
+//   4 mean2  5 istd2  6 k2a (= istd2)  7 k2b (= -mean2 istd2)
+// xh1 = z' k1a + k1b with z' = Wl.A;  y1 = g1 xh1 + be1;  r1 = relu(y1);  p = r1 V[i]
+// xh2 = p k2a + k2b;  y2 = g2 xh2 + be2;  h2 = relu(y2);  hm = h2 * keep * scale
+// ---------------------------------------------------------------------------------------
+
+template <int DPL, int WP>
+struct RowEval {
+    float wl[DPL][WP];
+    float k1a[DPL], k1b[DPL], g1[DPL], be1[DPL];
+    __device__ __forceinline__ void init(const HeadArgs& h, int lane) {
+        load_wl<DPL, WP>(h.Wl, h.W, lane, wl);
+        load_chan<DPL>(h.bnc + 2 * h.D, lane, k1a);
+        load_chan<DPL>(h.bnc + 3 * h.D, lane, k1b);
+        load_chan<DPL>(h.g1, lane, g1);
+        load_chan<DPL>(h.be1, lane, be1);
+    }
+    // xh1, y1 for the lane's channels
+    __device__ __forceinline__ void eval(const float (&a)[WP], float (&xh1)[DPL], float (&y1)[DPL]) const {
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            float z = 0.f;
+#pragma unroll
+            for (int w = 0; w < WP; ++w) z = fmaf(wl[j][w], a[w], z);
+            xh1[j] = fmaf(z, k1a[j], k1b[j]);
+            y1[j] = fmaf(g1[j], xh1[j], be1[j]);
+        }
+    }
+};
+
+#define GDN_TASK_LOOP_BEGIN(h)                                                                   \
+    const int lane = threadIdx.x & 31;                                                           \
+    const long long warp_ = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;             \
+    const long long nwarps_ = ((long long)gridDim.x * blockDim.x) >> 5;                          \
+    const long long tasks_ = (long long)(h).N * (h).S;                                           \
+    for (long long task_ = warp_; task_ < tasks_; task_ += nwarps_) {                            \
+        const int i = (int)(task_ / (h).S), sp = (int)(task_ % (h).S);                           \
+        const int b_lo = sp * (h).rps, b_hi = min((h).B, b_lo + (h).rps);
+#define GDN_TASK_LOOP_END }
+
+// BN2 batch statistics: sum_r p, sum_r p^2 -> part record [2*D] doubles
+template <int DPL, int WP>
+__global__ void __launch_bounds__(256)
+k_fwd_stats2(HeadArgs h, double* __restrict__ part) {
+    extern __shared__ double dsm[];
+    RowEval<DPL, WP> re;
+    re.init(h, threadIdx.x & 31);
+    double acc[2 * DPL];
+#pragma unroll
+    for (int q = 0; q < 2 * DPL; ++q) acc[q] = 0.0;
+    GDN_TASK_LOOP_BEGIN(h)
+        float v[DPL], s1[DPL], s2[DPL];
+        load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) s1[j] = s2[j] = 0.f;
+#pragma unroll 2
+        for (int b = b_lo; b < b_hi; ++b) {
+            float a[WP], xh1[DPL], y1[DPL];
+            load_arow<WP>(h.A + ((size_t)b * h.N + i) * h.W, h.W, a);
+            re.eval(a, xh1, y1);
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                const float p = fmaxf(y1[j], 0.f) * v[j];
+                s1[j] += p;
+                s2[j] = fmaf(p, p, s2[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) { acc[j] += (double)s1[j]; acc[DPL + j] += (double)s2[j]; }
+    GDN_TASK_LOOP_END
+    cta_reduce_channels<2 * DPL, DPL>(acc, h.D, part + (size_t)blockIdx.x * 2 * h.D, dsm);
+}
+
+template <int DPL>
+__device__ __forceinline__ void keep_flags(const HeadArgs& h, size_t r, int lane, bool (&keep)[DPL]) {
+    if (h.mask != nullptr) {
+        float m[DPL];
+        load_chan_vec<DPL>(h.mask + r * h.D, lane, m);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) keep[j] = m[j] != 0.f;
+    } else {
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            const unsigned long long e = (unsigned long long)r * h.D + (unsigned)(lane * DPL + j);
+            const int comp = (int)(e & 3ull);
+            if (j == 0 || comp == 0) rnd = philox4x32_10(e >> 2, h.offset, h.seed);
+            const uint32_t x = comp == 0 ? rnd.x : comp == 1 ? rnd.y : comp == 2 ? rnd.z : rnd.w;
+            keep[j] = u01(x) >= h.p_drop;
+        }
+    }
+}
+
+// pred[b,i] = sum_d hm[d] wo[d] + bo;  training: dropout + keep bits saved
+template <int DPL, int WP>
+__global__ void __launch_bounds__(256)
+k_fwd_out(HeadArgs h, float* __restrict__ pred) {
+    RowEval<DPL, WP> re;
+    re.init(h, threadIdx.x & 31);
+    float k2a[DPL], k2b[DPL], g2[DPL], be2[DPL], wo[DPL];
+    {
+        const int ln = threadIdx.x & 31;
+        load_chan<DPL>(h.bnc + 6 * h.D, ln, k2a);
+        load_chan<DPL>(h.bnc + 7 * h.D, ln, k2b);
+        load_chan<DPL>(h.g2, ln, g2);
+        load_chan<DPL>(h.be2, ln, be2);
+        load_chan<DPL>(h.wo, ln, wo);
+    }
+    const float bo = h.bo[0];
+    const bool drop = h.training && h.p_drop > 0.f;
+    GDN_TASK_LOOP_BEGIN(h)
+        float v[DPL];
+        load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
+#pragma unroll 2
+        for (int b = b_lo; b < b_hi; ++b) {
+            const size_t r = (size_t)b * h.N + i;
+            float a[WP], xh1[DPL], y1[DPL];
+            load_arow<WP>(h.A + r * h.W, h.W, a);
+            re.eval(a, xh1, y1);
+            bool keep[DPL];
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) keep[j] = true;
+            if (drop) {
+                keep_flags<DPL>(h, r, lane, keep);
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) {
+                    const uint32_t word = __ballot_sync(0xffffffffu, keep[j]);
+                    if (lane == j) h.bits[r * DPL + j] = word;
+                }
+            }
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                const float p = fmaxf(y1[j], 0.f) * v[j];
+                const float y2 = fmaf(g2[j], fmaf(p, k2a[j], k2b[j]), be2[j]);
+                float hm = fmaxf(y2, 0.f);
+                if (drop) hm = keep[j] ? hm * h.scale : 0.f;
+                dot = fmaf(hm, wo[j], dot);
+            }
+            dot = warp_sum(dot);
+            if (lane == 0) pred[r] = dot + bo;
+        }
+    GDN_TASK_LOOP_END
+}
+
+
+// shared recompute of the chain for the backward passes
+template <int DPL, int WP>
+struct BwdRow {
+    float k2a[DPL], k2b[DPL], g2[DPL], be2[DPL], wo[DPL];
+    __device__ __forceinline__ void init(const HeadArgs& h, int lane) {
+        load_chan<DPL>(h.bnc + 6 * h.D, lane, k2a);
+        load_chan<DPL>(h.bnc + 7 * h.D, lane, k2b);
+        load_chan<DPL>(h.g2, lane, g2);
+        load_chan<DPL>(h.be2, lane, be2);
+        load_chan<DPL>(h.wo, lane, wo);
+    }
+};
+
+template <int DPL>
+__device__ __forceinline__ void load_keep(const HeadArgs& h, size_t r, int lane, float (&kf)[DPL]) {
+    const bool drop = h.training && h.p_drop > 0.f;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+        if (drop) {
+            const uint32_t word = h.bits[r * DPL + j];
+            kf[j] = ((word >> lane) & 1u) ? h.scale : 0.f;
+        } else {
+            kf[j] = 1.f;
+        }
+    }
+}
+
+// pass 1: g_wo, g_gamma2, g_beta2, g_bo   -> part record [3*D + 32] doubles
+template <int DPL, int WP>
+__global__ void __launch_bounds__(256)
+k_bwd1(HeadArgs h, BwdArgs g, double* __restrict__ part) {
+    extern __shared__ double dsm[];
+    RowEval<DPL, WP> re;
+    BwdRow<DPL, WP> br;
+    re.init(h, threadIdx.x & 31);
+    br.init(h, threadIdx.x & 31);
+    double acc[3 * DPL];
+#pragma unroll
+    for (int q = 0; q < 3 * DPL; ++q) acc[q] = 0.0;
+    double gbo = 0.0;
+    GDN_TASK_LOOP_BEGIN(h)
+        float v[DPL], t0[DPL], t1[DPL], t2[DPL];
+        load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) t0[j] = t1[j] = t2[j] = 0.f;
+        float tb = 0.f;
+#pragma unroll 2
+        for (int b = b_lo; b < b_hi; ++b) {
+            const size_t r = (size_t)b * h.N + i;
+            float a[WP], xh1[DPL], y1[DPL], kf[DPL];
+            load_arow<WP>(h.A + r * h.W, h.W, a);
+            re.eval(a, xh1, y1);
+            load_keep<DPL>(h, r, lane, kf);
+            const float gp = g.gpred[r];
+            tb += gp;
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                const float p = fmaxf(y1[j], 0.f) * v[j];
+                const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
+                const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
+                const float hm = fmaxf(y2, 0.f) * kf[j];
+                t0[j] = fmaf(gp, hm, t0[j]);                                  // g_wo
+                const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
+                t1[j] = fmaf(gy2, xh2, t1[j]);                                // g_gamma2
+                t2[j] += gy2;                                                 // g_beta2
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            acc[j] += (double)t0[j]; acc[DPL + j] += (double)t1[j]; acc[2 * DPL + j] += (double)t2[j];
+        }
+        gbo += (double)tb;
+    GDN_TASK_LOOP_END
+    double* prec = part + (size_t)blockIdx.x * (3 * h.D + 32);
+    cta_reduce_channels<3 * DPL, DPL>(acc, h.D, prec, dsm);
+    // g_bo: every lane of a warp holds the same value; one slot per warp
+    if ((threadIdx.x & 31) == 0) dsm[threadIdx.x >> 5] = gbo;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += dsm[w];
+        prec[3 * h.D] = s;
+    }
+}
+
+// pass 2: g_V (sum over windows), g_gamma1, g_beta1     -> part record [2*D] doubles
+template <int DPL, int WP>
+__global__ void __launch_bounds__(256)
+k_bwd2(HeadArgs h, BwdArgs g, double* __restrict__ part) {
+    extern __shared__ double dsm[];
+    RowEval<DPL, WP> re;
+    BwdRow<DPL, WP> br;
+    re.init(h, threadIdx.x & 31);
+    br.init(h, threadIdx.x & 31);
+    float cB2[DPL], cG2[DPL], s2c[DPL];
+    {
+        const int ln = threadIdx.x & 31;
+        load_chan<DPL>(g.c2, ln, cB2);
+        load_chan<DPL>(g.c2 + h.D, ln, cG2);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) s2c[j] = br.g2[j] * br.k2a[j];
+    }
+    double acc[2 * DPL];
+#pragma unroll
+    for (int q = 0; q < 2 * DPL; ++q) acc[q] = 0.0;
+    GDN_TASK_LOOP_BEGIN(h)
+        float v[DPL], gv[DPL], t1[DPL], t2[DPL];
+        load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) gv[j] = t1[j] = t2[j] = 0.f;
+#pragma unroll 2
+        for (int b = b_lo; b < b_hi; ++b) {
+            const size_t r = (size_t)b * h.N + i;
+            float a[WP], xh1[DPL], y1[DPL], kf[DPL];
+            load_arow<WP>(h.A + r * h.W, h.W, a);
+            re.eval(a, xh1, y1);
+            load_keep<DPL>(h, r, lane, kf);
+            const float gp = g.gpred[r];
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                const float r1 = fmaxf(y1[j], 0.f);
+                const float p = r1 * v[j];
+                const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
+                const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
+                const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
+                const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);     // d loss / d p
+                gv[j] = fmaf(gpp, r1, gv[j]);
+                const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
+                t1[j] = fmaf(gy1, xh1[j], t1[j]);                             // g_gamma1
+                t2[j] += gy1;                                                 // g_beta1
+            }
+        }
+        store_chan<DPL>(g.gV + ((size_t)sp * h.N + i) * h.D, lane, gv);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) { acc[j] += (double)t1[j]; acc[DPL + j] += (double)t2[j]; }
+    GDN_TASK_LOOP_END
+    cta_reduce_channels<2 * DPL, DPL>(acc, h.D, part + (size_t)blockIdx.x * 2 * h.D, dsm);
+}
+
+// pass 3: g_A[r,:] = g_z.Wl, partial g_Wl += g_z (x) A, partial g_bias += g_z
+// part record: [D*W + D] doubles
+template <int DPL, int WP>
+__global__ void __launch_bounds__(256)
+k_bwd3(HeadArgs h, BwdArgs g, double* __restrict__ part) {
+    __shared__ float red[8][33][32];
+    RowEval<DPL, WP> re;
+    BwdRow<DPL, WP> br;
+    re.init(h, threadIdx.x & 31);
+    br.init(h, threadIdx.x & 31);
+    const int wid = threadIdx.x >> 5;
+    float cB2[DPL], cG2[DPL], s2c[DPL], cB1[DPL], cG1[DPL], s1c[DPL];
+    {
+        const int ln = threadIdx.x & 31;
+        load_chan<DPL>(g.c2, ln, cB2);
+        load_chan<DPL>(g.c2 + h.D, ln, cG2);
+        load_chan<DPL>(g.c1, ln, cB1);
+        load_chan<DPL>(g.c1 + h.D, ln, cG1);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) { s2c[j] = br.g2[j] * br.k2a[j]; s1c[j] = re.g1[j] * re.k1a[j]; }
+    }
+    float gwl[DPL][WP], gb[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+        gb[j] = 0.f;
+#pragma unroll
+        for (int w = 0; w < WP; ++w) gwl[j][w] = 0.f;
+    }
+    GDN_TASK_LOOP_BEGIN(h)
+        float v[DPL];
+        load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
+        for (int b = b_lo; b < b_hi; ++b) {
+            const size_t r = (size_t)b * h.N + i;
+            float a[WP], xh1[DPL], y1[DPL], kf[DPL], pw[WP];
+            load_arow<WP>(h.A + r * h.W, h.W, a);
+            re.eval(a, xh1, y1);
+            load_keep<DPL>(h, r, lane, kf);
+            const float gp = g.gpred[r];
+#pragma unroll
+            for (int w = 0; w < WP; ++w) pw[w] = 0.f;
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                const float p = fmaxf(y1[j], 0.f) * v[j];
+                const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
+                const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
+                const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
+                const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);
+                const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
+                const float gz = s1c[j] * (gy1 - cB1[j] - xh1[j] * cG1[j]);   // d loss / d z
+                gb[j] += gz;
+#pragma unroll
+                for (int w = 0; w < WP; ++w) {
+                    pw[w] = fmaf(gz, re.wl[j][w], pw[w]);
+                    gwl[j][w] = fmaf(gz, a[w], gwl[j][w]);
+                }
+            }
+            int widx;
+            const float tot = reduce_scatter<WP>(pw, lane, &widx);
+            if ((lane & ((32 / WP) - 1)) == 0 && widx < h.W) g.gA[r * h.W + widx] = tot;
+        }
+    GDN_TASK_LOOP_END
+    double* prec = part + (size_t)blockIdx.x * ((size_t)h.D * h.W + h.D);
+    const int ln = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+#pragma unroll
+        for (int w = 0; w < WP; ++w) red[wid][w][ln] = gwl[j][w];
+        red[wid][32][ln] = gb[j];
+        __syncthreads();
+        for (int e = threadIdx.x; e < 33 * 32; e += blockDim.x) {
+            const int w = e >> 5, l = e & 31;
+            if (w < h.W || w == 32) {
+                double s = 0.0;
+                for (int q = 0; q < 8; ++q) s += (double)red[q][w][l];
+                const int d = l * DPL + j;
+                if (w == 32) prec[(size_t)h.D * h.W + d] = s;
+                else prec[(size_t)d * h.W + w] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize kernels (one CTA, 256 threads)
+// ---------------------------------------------------------------------------------------
+// BN1 statistics from the moments of A; writes ctx.bn[0..3], updates running stats.
+__global__ void k_fin_bn1(const double* __restrict__ part, int nrec, long long n, int W, int D,
+                          const float* __restrict__ Wl, const float* __restrict__ bias,
+                          float* __restrict__ bnc, float* __restrict__ rmean, float* __restrict__ rvar,
+                          long long* __restrict__ nbt) {
+    extern __shared__ double sm[];          // [W*W + W]
+    const int rec = W * W + W;
+    for (int e = threadIdx.x; e < rec; e += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nrec; ++q) s += part[(size_t)q * rec + e];
+        sm[e] = s / (double)n;
+    }
+    __syncthreads();
+    const double* m2 = sm;                  // E[a_w a_w']
+    const double* m1 = sm + W * W;          // E[a_w]
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        double mean = bias ? (double)bias[d] : 0.0, var = 0.0;
+        for (int w = 0; w < W; ++w) {
+            const double wl = (double)Wl[(size_t)d * W + w];
+            mean += wl * m1[w];
+            double row = 0.0;
+            for (int w2 = 0; w2 < W; ++w2)
+                row += (m2[w * W + w2] - m1[w] * m1[w2]) * (double)Wl[(size_t)d * W + w2];
+            var += wl * row;
+        }
+        if (var < 0.0) var = 0.0;
+        const double istd = 1.0 / sqrt(var + (double)GDN_BN_EPS);
+        bnc[d] = (float)mean;
+        bnc[D + d] = (float)istd;
+        bnc[2 * D + d] = (float)istd;
+        bnc[3 * D + d] = (float)(((bias ? (double)bias[d] : 0.0) - mean) * istd);
+        if (rmean != nullptr) {
+            const double unb = n > 1 ? var * (double)n / (double)(n - 1) : var;
+            rmean[d] = (1.f - GDN_BN_MOMENTUM) * rmean[d] + GDN_BN_MOMENTUM * (float)mean;
+            rvar[d] = (1.f - GDN_BN_MOMENTUM) * rvar[d] + GDN_BN_MOMENTUM * (float)unb;
+        }
+    }
+    if (threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+}
+
+// BN2 statistics from sum p, sum p^2; writes ctx.bn[4..7], updates running stats.
+__global__ void k_fin_bn2(const double* __restrict__ part, int nrec, long long n, int D,
+                          float* __restrict__ bnc, float* __restrict__ rmean, float* __restrict__ rvar,
+                          long long* __restrict__ nbt) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int q = 0; q < nrec; ++q) { s1 += part[(size_t)q * 2 * D + d]; s2 += part[(size_t)q * 2 * D + D + d]; }
+        const double mean = s1 / (double)n;
+        double var = s2 / (double)n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double istd = 1.0 / sqrt(var + (double)GDN_BN_EPS);
+        bnc[4 * D + d] = (float)mean;
+        bnc[5 * D + d] = (float)istd;
+        bnc[6 * D + d] = (float)istd;
+        bnc[7 * D + d] = (float)(-mean * istd);
+        if (rmean != nullptr) {
+            const double unb = n > 1 ? var * (double)n / (double)(n - 1) : var;
+            rmean[d] = (1.f - GDN_BN_MOMENTUM) * rmean[d] + GDN_BN_MOMENTUM * (float)mean;
+            rvar[d] = (1.f - GDN_BN_MOMENTUM) * rvar[d] + GDN_BN_MOMENTUM * (float)unb;
+        }
+    }
+    if (threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+}
+
+// eval mode: constants from the running statistics (both BNs)
+__global__ void k_fin_bn_eval(int D, const float* __restrict__ bias,
+                              const float* __restrict__ rm1, const float* __restrict__ rv1,
+                              const float* __restrict__ rm2, const float* __restrict__ rv2,
+                              float* __restrict__ bnc) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float i1 = 1.f / sqrtf(rv1[d] + GDN_BN_EPS);
+        const float i2 = 1.f / sqrtf(rv2[d] + GDN_BN_EPS);
+        bnc[d] = rm1[d]; bnc[D + d] = i1; bnc[2 * D + d] = i1;
+        bnc[3 * D + d] = ((bias ? bias[d] : 0.f) - rm1[d]) * i1;
+        bnc[4 * D + d] = rm2[d]; bnc[5 * D + d] = i2; bnc[6 * D + d] = i2;
+        bnc[7 * D + d] = -rm2[d] * i2;
+    }
+}
+
+// pass-1 sums -> g_wo, g_gamma2, g_beta2, g_bo and the pass-2 coefficients c2 = (g_beta2/n, g_gamma2/n)
+__global__ void k_fin_bwd1(const double* __restrict__ part, int nrec, long long n, int D,
+                           float* __restrict__ g_wo, float* __restrict__ g_g2, float* __restrict__ g_b2,
+                           float* __restrict__ g_bo, float* __restrict__ c2) {
+    const int rec = 3 * D + 32;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        double a = 0.0, b = 0.0, c = 0.0;
+        for (int q = 0; q < nrec; ++q) {
+            a += part[(size_t)q * rec + d]; b += part[(size_t)q * rec + D + d]; c += part[(size_t)q * rec + 2 * D + d];
+        }
+        g_wo[d] = (float)a; g_g2[d] = (float)b; g_b2[d] = (float)c;
+        c2[d] = (float)(c / (double)n);
+        c2[D + d] = (float)(b / (double)n);
+    }
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int q = 0; q < nrec; ++q) s += part[(size_t)q * rec + 3 * D];
+        g_bo[0] = (float)s;
+    }
+}
+
+__global__ void k_fin_bwd2(const double* __restrict__ part, int nrec, long long n, int D,
+                           float* __restrict__ g_g1, float* __restrict__ g_b1, float* __restrict__ c1) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        double b = 0.0, c = 0.0;
+        for (int q = 0; q < nrec; ++q) { b += part[(size_t)q * 2 * D + d]; c += part[(size_t)q * 2 * D + D + d]; }
+        g_g1[d] = (float)b; g_b1[d] = (float)c;
+        c1[d] = (float)(c / (double)n);
+        c1[D + d] = (float)(b / (double)n);
+    }
+}
+
+// sum the S partial embedding gradients
+__global__ void k_reduce_gV(const float* __restrict__ gVp, int S, long long ND, float* __restrict__ gV) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ND; e += (long long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int q = 0; q < S; ++q) s += gVp[(size_t)q * ND + e];
+        gV[e] = s;
+    }
+}
+
+// layer parameter gradients:
+//   g_Wl[d,w] = main[d,w] + a_i[d] g_ui[w] + a_j[d] g_uj[w];  g_bias = main
+//   g_a_i[d] = sum_w Wl[d,w] g_ui[w];  g_a_j likewise
+__global__ void k_fin_layer(const double* __restrict__ part, int nrec,
+                            const float* __restrict__ part_u, int nrec_u, int W, int D,
+                            const float* __restrict__ Wl, const float* __restrict__ a_i, const float* __restrict__ a_j,
+                            float* __restrict__ g_Wl, float* __restrict__ g_bias,
+                            float* __restrict__ g_ai, float* __restrict__ g_aj) {
+    __shared__ double gu[64];
+    if (threadIdx.x < 64) {
+        double s = 0.0;
+        for (int q = 0; q < nrec_u; ++q) s += (double)part_u[(size_t)q * 64 + threadIdx.x];
+        gu[threadIdx.x] = s;
+    }
+    __syncthreads();
+    const size_t rec = (size_t)D * W + D;
+    for (int e = threadIdx.x; e < D * W + D; e += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nrec; ++q) s += part[(size_t)q * rec + e];
+        if (e < D * W) {
+            const int d = e / W, w = e % W;
+            s += (double)a_i[d] * gu[w] + (double)a_j[d] * gu[32 + w];
+            g_Wl[e] = (float)s;
+        } else if (g_bias != nullptr) {
+            g_bias[e - D * W] = (float)s;
+        }
+    }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        double si = 0.0, sj = 0.0;
+        for (int w = 0; w < W; ++w) {
+            const double wl = (double)Wl[(size_t)d * W + w];
+            si += wl * gu[w];
+            sj += wl * gu[32 + w];
+        }
+        g_ai[d] = (float)si;
+        g_aj[d] = (float)sj;
+    }
+}
+
+__global__ void k_fin_embed(const float* __restrict__ part, int nrec, int D,
+                            float* __restrict__ g_aei, float* __restrict__ g_aej) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        double si = 0.0, sj = 0.0;
+        for (int q = 0; q < nrec; ++q) { si += (double)part[(size_t)q * 2 * D + d]; sj += (double)part[(size_t)q * 2 * D + D + d]; }
+        g_aei[d] = (float)si;
+        g_aej[d] = (float)sj;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------
+#define GDN_DISPATCH_DW(DPLV, WPV, CALL)                                             \
+    do {                                                                              \
+        if (DPLV == 1) { GDN_DISPATCH_W(1, WPV, CALL); }                              \
+        else if (DPLV == 2) { GDN_DISPATCH_W(2, WPV, CALL); }                         \
+        else if (DPLV == 4) { GDN_DISPATCH_W(4, WPV, CALL); }                         \
+        else { GDN_DISPATCH_W(8, WPV, CALL); }                                        \
+    } while (0)
+#define GDN_DISPATCH_W(DPLC, WPV, CALL)                                               \
+    do {                                                                              \
+        if (WPV == 8) { CALL(DPLC, 8); }                                              \
+        else if (WPV == 16) { CALL(DPLC, 16); }                                       \
+        else { CALL(DPLC, 32); }                                                      \
+    } while (0)
+
+static int dw_grid(long long tasks) {
+    long long g = (tasks + 7) / 8;
+    const int cap = 2 * num_sms();
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+int launch_lin_fwd(const Shape& s, const float* A, const gdn_layer_params* p, float* out, cudaStream_t st) {
+    const int grid = dw_grid(s.n);
+#define CALL(DPLC, WPC) k_lin_fwd<DPLC, WPC><<<grid, 256, 0, st>>>(A, p->lin_weight, p->bias, s.n, s.W, s.D, out)
+    GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
+#undef CALL
+    GDN_CHECK_LAUNCH("k_lin_fwd");
+    return 0;
+}
+
+int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_layer_params* p, float* gA,
+                   double* part, int* nrec, cudaStream_t st) {
+    const int grid = dw_grid(s.n);
+#define CALL(DPLC, WPC) k_lin_bwd<DPLC, WPC><<<grid, 256, 0, st>>>(gout, A, p->lin_weight, s.n, s.W, s.D, gA, part)
+    GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
+#undef CALL
+    GDN_CHECK_LAUNCH("k_lin_bwd");
+    *nrec = grid;
+    return 0;
+}
+
+int launch_moments(const Shape& s, const float* A, double* part, int* nrec, cudaStream_t st) {
+    const int grid = dw_grid((s.n + 3) / 4);
+    if (s.WP == 8) k_moments<8><<<grid, 256, 0, st>>>(A, s.n, s.W, part);
+    else if (s.WP == 16) k_moments<16><<<grid, 256, 0, st>>>(A, s.n, s.W, part);
+    else k_moments<32><<<grid, 128, 0, st>>>(A, s.n, s.W, part);
+    GDN_CHECK_LAUNCH("k_moments");
+    *nrec = grid;
+    return 0;
+}
+
+int launch_fin_bn1(const Shape& s, const double* part, int nrec, const gdn_layer_params* p, float* bnc,
+                   const gdn_bn* bn, cudaStream_t st) {
+    const size_t smem = ((size_t)s.W * s.W + s.W) * sizeof(double);
+    k_fin_bn1<<<1, 256, smem, st>>>(part, nrec, s.n, s.W, s.D, p->lin_weight, p->bias, bnc,
+                                    bn->running_mean, bn->running_var, (long long*)bn->num_batches_tracked);
+    GDN_CHECK_LAUNCH("k_fin_bn1");
+    return 0;
+}
+
+int launch_fin_bn_eval(const Shape& s, const gdn_layer_params* p, const gdn_head_params* h, float* bnc,
+                       cudaStream_t st) {
+    k_fin_bn_eval<<<1, 256, 0, st>>>(s.D, p->bias, h->bn1.running_mean, h->bn1.running_var,
+                                     h->bn2.running_mean, h->bn2.running_var, bnc);
+    GDN_CHECK_LAUNCH("k_fin_bn_eval");
+    return 0;
+}
+
+static size_t dsm_bytes(int nv) { return (size_t)8 * nv * 32 * sizeof(double); }
+
+int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, const gdn_bn* bn, float* bnc,
+                      cudaStream_t st) {
+    const int grid = dw_grid((long long)s.N * s.S);
+#define CALL(DPLC, WPC)                                                                                   \
+    do {                                                                                                  \
+        const size_t sm = dsm_bytes(2 * DPLC);                                                            \
+        if (sm > 48 * 1024)                                                                               \
+            cudaFuncSetAttribute(k_fwd_stats2<DPLC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        k_fwd_stats2<DPLC, WPC><<<grid, 256, sm, st>>>(h, part);                                          \
+    } while (0)
+    GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
+#undef CALL
+    GDN_CHECK_LAUNCH("k_fwd_stats2");
+    k_fin_bn2<<<1, 256, 0, st>>>(part, grid, s.n, s.D, bnc, bn->running_mean, bn->running_var,
+                                 (long long*)bn->num_batches_tracked);
+    GDN_CHECK_LAUNCH("k_fin_bn2");
+    return 0;
+}
+
+int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t st) {
+    const int grid = dw_grid((long long)s.N * s.S);
+#define CALL(DPLC, WPC) k_fwd_out<DPLC, WPC><<<grid, 256, 0, st>>>(h, pred)
+    GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
+#undef CALL
+    GDN_CHECK_LAUNCH("k_fwd_out");
+    return 0;
+}
+
+int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, gdn_head_grads* gh,
+                float* c2, cudaStream_t st) {
+    const int grid = dw_grid((long long)s.N * s.S);
+#define CALL(DPLC, WPC)                                                                                 \
+    do {                                                                                                \
+        const size_t sm = dsm_bytes(3 * DPLC);                                                          \
+        if (sm > 48 * 1024)                                                                             \
+            cudaFuncSetAttribute(k_bwd1<DPLC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        k_bwd1<DPLC, WPC><<<grid, 256, sm, st>>>(h, g, part);                                           \
+    } while (0)
+    GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
+#undef CALL
+    GDN_CHECK_LAUNCH("k_bwd1");
+    k_fin_bwd1<<<1, 256, 0, st>>>(part, grid, s.n, s.D, gh->out_w, gh->bn2_weight, gh->bn2_bias, gh->out_b, c2);
+    GDN_CHECK_LAUNCH("k_fin_bwd1");
+    return 0;
+}
+
+int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, gdn_head_grads* gh,
+                float* c1, float* gV_final, cudaStream_t st) {
+    const int grid = dw_grid((long long)s.N * s.S);
+#define CALL(DPLC, WPC)                                                                                 \
+    do {                                                                                                \
+        const size_t sm = dsm_bytes(2 * DPLC);                                                          \
+        if (sm > 48 * 1024)                                                                             \
+            cudaFuncSetAttribute(k_bwd2<DPLC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        k_bwd2<DPLC, WPC><<<grid, 256, sm, st>>>(h, g, part);                                           \
+    } while (0)
+    GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
+#undef CALL
+    GDN_CHECK_LAUNCH("k_bwd2");
+    k_fin_bwd2<<<1, 256, 0, st>>>(part, grid, s.n, s.D, gh->bn1_weight, gh->bn1_bias, c1);
+    GDN_CHECK_LAUNCH("k_fin_bwd2");
+    if (s.S > 1) {
+        const long long ND = (long long)s.N * s.D;
+        int gr = (int)((ND + 255) / 256);
+        if (gr > 8 * num_sms()) gr = 8 * num_sms();
+        k_reduce_gV<<<gr, 256, 0, st>>>(g.gV, s.S, ND, gV_final);
+        GDN_CHECK_LAUNCH("k_reduce_gV");
+    }
+    return 0;
+}
+
+int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st) {
+    const int grid = dw_grid((long long)s.N * s.S);
+#define CALL(DPLC, WPC) k_bwd3<DPLC, WPC><<<grid, 256, 0, st>>>(h, g, part)
+    GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
+#undef CALL
+    GDN_CHECK_LAUNCH("k_bwd3");
+    *nrec = grid;
+    return 0;
+}
+
+int launch_fin_layer(const Shape& s, const double* part, int nrec, const float* part_u, int nrec_u,
+                     const gdn_layer_params* p, gdn_layer_grads* g, cudaStream_t st) {
+    k_fin_layer<<<1, 256, 0, st>>>(part, nrec, part_u, nrec_u, s.W, s.D, p->lin_weight, p->att_i, p->att_j,
+                                   g->lin_weight, g->bias, g->att_i, g->att_j);
+    GDN_CHECK_LAUNCH("k_fin_layer");
+    return 0;
+}
+
+int launch_fin_embed(const Shape& s, const float* part, int nrec, gdn_layer_grads* g, cudaStream_t st) {
+    k_fin_embed<<<1, 256, 0, st>>>(part, nrec, s.D, g->att_em_i, g->att_em_j);
+    GDN_CHECK_LAUNCH("k_fin_embed");
+    return 0;
+}
+
+}  // namespace gdn

@@ -1,0 +1,72 @@
+// launchers.h -- host-side launch functions shared between the translation units.
+#pragma once
+#include "common.cuh"
+
+namespace gdn {
+
+// mirrors of the kernel argument structs in dwide.cu
+struct HeadArgs {
+    const float* A;
+    const float* V;
+    const float* Wl;
+    const float* bnc;
+    const float* g1; const float* be1; const float* g2; const float* be2;
+    const float* wo; const float* bo;
+    int B, N, W, D, S, rps;
+    const float* mask;
+    uint32_t* bits;
+    unsigned long long seed, offset;
+    float p_drop, scale;
+    int training;
+};
+struct BwdArgs {
+    const float* gpred;
+    const float* c2;
+    const float* c1;
+    float* gV;
+    float* gA;
+};
+
+// attention.cu
+int launch_prep(const Shape& s, const float* x, const float* V, const gdn_layer_params* p,
+                char* ctx, const CtxLayout& L, cudaStream_t st);
+int launch_attn_fwd(const Shape& s, const int32_t* nbr, char* ctx, const CtxLayout& L, float* alpha, cudaStream_t st);
+int launch_attn_alpha(const Shape& s, const int32_t* nbr, const char* ctx, const CtxLayout& L, float* alpha,
+                      cudaStream_t st);
+int launch_attn_bwd(const Shape& s, const int32_t* nbr, const char* ctx, const CtxLayout& L,
+                    const float* gA, float* gsiT, float* gsjT, float* gev, float* part_u, int* n_part_u,
+                    cudaStream_t st);
+int launch_embed_grads(const Shape& s, const float* V, const float* gev, const gdn_layer_params* p,
+                       int accumulate, float* gV, float* part, int* n_part, cudaStream_t st);
+
+// dwide.cu
+int launch_lin_fwd(const Shape& s, const float* A, const gdn_layer_params* p, float* out, cudaStream_t st);
+int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_layer_params* p, float* gA,
+                   double* part, int* nrec, cudaStream_t st);
+int launch_moments(const Shape& s, const float* A, double* part, int* nrec, cudaStream_t st);
+int launch_fin_bn1(const Shape& s, const double* part, int nrec, const gdn_layer_params* p, float* bnc,
+                   const gdn_bn* bn, cudaStream_t st);
+int launch_fin_bn_eval(const Shape& s, const gdn_layer_params* p, const gdn_head_params* h, float* bnc,
+                       cudaStream_t st);
+int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, const gdn_bn* bn, float* bnc, cudaStream_t st);
+int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t st);
+int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, gdn_head_grads* gh, float* c2,
+                cudaStream_t st);
+int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, gdn_head_grads* gh, float* c1,
+                float* gV_final, cudaStream_t st);
+int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st);
+int launch_fin_layer(const Shape& s, const double* part, int nrec, const float* part_u, int nrec_u,
+                     const gdn_layer_params* p, gdn_layer_grads* g, cudaStream_t st);
+int launch_fin_embed(const Shape& s, const float* part, int nrec, gdn_layer_grads* g, cudaStream_t st);
+
+// graph_build.cu
+size_t graph_build_ws_bytes(int N, int D, int K);
+int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, size_t ws_bytes,
+                       int use_tc, cudaStream_t st);
+
+// scoring.cu
+size_t score_ws_bytes(int T, int N);
+int launch_score(const float* pred, const float* gt, int T, int N, double* scores, double* top1, double* stats,
+                 void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace gdn

@@ -1,0 +1,179 @@
+/* gdn_b200.h -- C ABI of libgdn_b200.so: the B200 (sm_100a) implementation of the GDN
+ * forward/backward hot path (reference: SchlomoFeng/GDN).
+ *
+ * The reference is pure Python on top of PyTorch + torch-geometric 1.5.0; it has no FFI
+ * of its own.  The entry points below are what a binding for this path replaces, one
+ * per reference call site (file:line under the reference tree):
+ *
+ *   gdn_graph_build        models/GDN.py:143-159   cosine Gram + row-wise top-k
+ *   gdn_graphlayer_fwd     models/graph_layer.py:53-117 (+ PyG propagate/softmax) on the
+ *                          window-shared top-k graph built by models/GDN.py:161-165
+ *   gdn_graphlayer_bwd     autograd of the above (train.py:72)
+ *   gdn_csr_fwd / _bwd     models/graph_layer.py:53-117 on an arbitrary edge list
+ *   gdn_fused_fwd          models/GDN.py:122-187 (GraphLayer + BN + ReLU + (x)embedding +
+ *                          BN + ReLU + Dropout + Linear(D,1)), train or eval
+ *   gdn_fused_bwd          autograd of models/GDN.py:122-187 (train.py:72)
+ *   gdn_score              evaluate.py:48-68 + util/data.py:75-82 (+ evaluate.py:134-139)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_; the library
+ *     never allocates, frees or retains device memory: the caller owns every buffer,
+ *     including the scratch `ws` and the saved-for-backward `ctx` blobs whose sizes the
+ *     *_bytes() queries return;
+ *   - all tensors are dense, row-major, float32 unless stated; sizes are ints;
+ *   - `stream` is a cudaStream_t passed as void*; every kernel is enqueued on it and the
+ *     call returns without synchronising (CUDA-graph capturable);
+ *   - return value: 0 = ok, <0 = invalid argument / unsupported shape, >0 = cudaError_t;
+ *     gdn_last_error() returns a thread-local message for the last non-zero return.
+ *   - there is no CPU fallback anywhere.
+ */
+#ifndef GDN_B200_H
+#define GDN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDN_B200_VERSION 100
+
+/* Problem shape shared by the window-batched entry points.
+ * n = B*N rows; the neighbour table `nbr` has Kp = K+1 slots per sensor. */
+typedef struct gdn_dims {
+    int B;   /* windows in the batch                          */
+    int N;   /* sensors (node_num)                            */
+    int W;   /* slide_win = GraphLayer in_channels  (<= 32)   */
+    int D;   /* dim = GraphLayer out_channels       (<= 256, multiple of 4) */
+    int K;   /* topk                                          */
+} gdn_dims;
+
+/* GraphLayer parameters (models/graph_layer.py:25-36), heads = 1. */
+typedef struct gdn_layer_params {
+    const float* lin_weight; /* [D, W]  gnn.lin.weight                      */
+    const float* att_i;      /* [D]     gnn.att_i  (1,1,D flattened)        */
+    const float* att_j;      /* [D]                                         */
+    const float* att_em_i;   /* [D]                                         */
+    const float* att_em_j;   /* [D]                                         */
+    const float* bias;       /* [D]     gnn.bias (may be NULL)              */
+} gdn_layer_params;
+
+typedef struct gdn_layer_grads {
+    float* lin_weight; /* [D, W] */
+    float* att_i;      /* [D]    */
+    float* att_j;      /* [D]    */
+    float* att_em_i;   /* [D]    */
+    float* att_em_j;   /* [D]    */
+    float* bias;       /* [D] (may be NULL) */
+    float* embedding;  /* [N, D] gradient w.r.t. the sensor embedding V (overwritten) */
+} gdn_layer_grads;
+
+/* BatchNorm1d(D) state (models/GDN.py:67 and :96). */
+typedef struct gdn_bn {
+    const float* weight;        /* [D] gamma */
+    const float* bias;          /* [D] beta  */
+    float* running_mean;        /* [D] updated in training mode            */
+    float* running_var;         /* [D] updated in training mode (unbiased) */
+    int64_t* num_batches_tracked; /* scalar, += 1 in training mode (may be NULL) */
+} gdn_bn;
+
+/* Head of the model for out_layer_num == 1 (models/GDN.py:36,171-187). */
+typedef struct gdn_head_params {
+    gdn_bn bn1;            /* gnn_layers.0.bn                 */
+    gdn_bn bn2;            /* bn_outlayer_in                  */
+    const float* out_w;    /* [D] out_layer.mlp.0.weight      */
+    const float* out_b;    /* [1] out_layer.mlp.0.bias        */
+} gdn_head_params;
+
+typedef struct gdn_head_grads {
+    float* bn1_weight; float* bn1_bias;   /* [D] each */
+    float* bn2_weight; float* bn2_bias;   /* [D] each */
+    float* out_w;                         /* [D] */
+    float* out_b;                         /* [1] */
+} gdn_head_grads;
+
+/* Dropout(0.2) (models/GDN.py:114,182).  Either an explicit keep-mask (test hook:
+ * values in {0, 1/(1-p)}, layout [B, N, D]) or counter-based Philox4x32-10 keyed by
+ * (seed, offset): element (b, i, d) uses counter ((b*N+i)*D + d) / 4, lane % 4. */
+typedef struct gdn_dropout {
+    const float* mask;   /* NULL -> Philox */
+    uint64_t seed;
+    uint64_t offset;
+    float p;             /* 0 disables dropout */
+} gdn_dropout;
+
+int         gdn_version(void);
+const char* gdn_last_error(void);
+
+/* ---- a1: learned graph (models/GDN.py:143-159) ---------------------------------------
+ * V [N, D] -> idx [N, K] int64 (torch.topk order: descending cosine, ties -> lower index)
+ *          and nbr [N, K+1] int32: the neighbour list GraphLayer actually uses after
+ *          remove_self_loops/add_self_loops (models/graph_layer.py:61-63): the non-self
+ *          top-k entries in order, then the sensor itself, then -1 padding.
+ * Either output may be NULL.  use_tensor_cores: 0 = exact fp32 CUDA-core Gram,
+ * 1 = tcgen05 split-precision Gram with exact fp32 re-scoring, -1 = choose by N. */
+size_t gdn_graph_build_ws_bytes(int N, int D, int K);
+int    gdn_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr,
+                       void* ws, size_t ws_bytes, int use_tensor_cores, void* stream);
+
+/* ---- a3/a4: GraphLayer on the window-shared graph ------------------------------------
+ * x [B, N, W], V [N, D], nbr [N, K+1] -> out [B*N, D]
+ * alpha (optional) [B*N, K+1]: attention weight of slot k of row (b, i) (0 for padding).
+ * ctx: saved-for-backward blob of gdn_graphlayer_ctx_bytes(); ws: scratch. */
+size_t gdn_graphlayer_ctx_bytes(const gdn_dims* d);
+size_t gdn_graphlayer_ws_bytes(const gdn_dims* d);
+int    gdn_graphlayer_fwd(const gdn_dims* d, const float* x, const float* V, const int32_t* nbr,
+                          const gdn_layer_params* p, float* out, float* alpha,
+                          void* ctx, void* ws, size_t ws_bytes, void* stream);
+int    gdn_graphlayer_bwd(const gdn_dims* d, const float* g_out, const float* V, const int32_t* nbr,
+                          const gdn_layer_params* p, const void* ctx, gdn_layer_grads* g,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* ---- a3/a4 on an arbitrary edge list (GraphLayer's own module boundary) ----------------
+ * CSR by target: rowptr [n+1], col [E] (sources; self loops already fixed up by the
+ * caller exactly as models/graph_layer.py:61-63 does), heads >= 1.
+ * x [n, W], emb [n, D] (may be NULL... the reference requires it), lin_weight [H*D, W],
+ * att_* [H*D], out_h [n, H, D] (per-head aggregate; the caller applies concat/mean+bias),
+ * alpha [E, H]. */
+int    gdn_csr_fwd(int n, int W, int D, int H, int64_t E, const int32_t* rowptr, const int32_t* col,
+                   const float* x, const float* emb, const float* lin_weight,
+                   const float* att_i, const float* att_j, const float* att_em_i, const float* att_em_j,
+                   float* xl /*[n,H*D] scratch+saved*/, float* s_i /*[n,H]*/, float* s_j /*[n,H]*/,
+                   float* out_h, float* alpha, float negative_slope, void* stream);
+int    gdn_csr_bwd(int n, int W, int D, int H, int64_t E, const int32_t* rowptr, const int32_t* col,
+                   const float* x, const float* emb, const float* lin_weight,
+                   const float* att_i, const float* att_j, const float* att_em_i, const float* att_em_j,
+                   const float* xl, const float* s_i, const float* s_j, const float* alpha,
+                   const float* g_out_h /*[n,H,D]*/,
+                   float* g_xl /*[n,H*D] scratch*/, float* g_si /*[n,H]*/, float* g_sj /*[n,H]*/,
+                   float negative_slope, void* stream);
+
+/* ---- a3-a7: whole GDN forward / backward, out_layer_num == 1 ---------------------------
+ * training != 0: batch statistics + running-stat update + dropout; else running stats.
+ * pred [B, N].  ctx keeps what the backward needs; ws is scratch. */
+size_t gdn_fused_ctx_bytes(const gdn_dims* d);
+size_t gdn_fused_ws_bytes(const gdn_dims* d);
+int    gdn_fused_fwd(const gdn_dims* d, const float* x, const float* V, const int32_t* nbr,
+                     const gdn_layer_params* p, const gdn_head_params* h, const gdn_dropout* dp,
+                     int training, float* pred, void* ctx, void* ws, size_t ws_bytes, void* stream);
+int    gdn_fused_bwd(const gdn_dims* d, const float* g_pred, const float* V, const int32_t* nbr,
+                     const gdn_layer_params* p, const gdn_head_params* h, const gdn_dropout* dp,
+                     const void* ctx, gdn_layer_grads* g, gdn_head_grads* gh,
+                     void* ws, size_t ws_bytes, void* stream);
+/* attention weights of the last gdn_fused_fwd / gdn_graphlayer_fwd held in ctx:
+ * alpha [B*N, K+1] (GNNLayer.att_weight_1, materialised only on demand). */
+int    gdn_ctx_alpha(const gdn_dims* d, const int32_t* nbr, const void* ctx, float* alpha, void* stream);
+
+/* ---- a8: test-time scoring (evaluate.py:48-68, util/data.py:75-82) ---------------------
+ * pred, gt [T, N] float32 -> scores [N, T] float64 (normalised, smoothed error per sensor)
+ * and top1 [T] float64 (max over sensors, evaluate.py:134-139 with topk=1); either may be
+ * NULL.  stats (optional) [N, 2] float64 = (median, IQR) per sensor. */
+size_t gdn_score_ws_bytes(int T, int N);
+int    gdn_score(const float* pred, const float* gt, int T, int N, double* scores, double* top1,
+                 double* stats, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDN_B200_H */
