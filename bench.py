@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the GDN hot path on B200 (see the contract in DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1..C5] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one training step of GDN on one batch of synthetic windows per GPU:
+zero_grad -> forward -> MSE -> backward -> (flat gradient all-reduce) -> Adam step
+(train.py:68-73 of the reference).  The default workload is the per-GPU shard of
+BASELINE.json configs[4] (16384 sensors, slide_win 16, dim 128, topk 64, 64 windows per GPU:
+global batch 512 at 8 GPUs, weak scaling); `--workload C1..C4` selects the other configs.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C1": dict(N=27, W=5, D=64, K=5, B=32, cpu_B=32, desc="MSL demo (run.sh)"),
+    "C2": dict(N=51, W=5, D=64, K=15, B=128, cpu_B=128, desc="SWaT-shaped"),
+    "C3": dict(N=127, W=5, D=128, K=30, B=256, cpu_B=64, desc="WADI-shaped"),
+    "C4": dict(N=4096, W=16, D=128, K=32, B=64, cpu_B=2, desc="scale-up synthetic"),
+    "C5": dict(N=16384, W=16, D=128, K=64, B=64, cpu_B=1, desc="8xB200 data-parallel config, per-GPU shard"),
+}
+METRIC = "train windows/sec"
+UNIT = "windows/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="C5", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the GraphLayer / score / profile legs")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    return ap.parse_args()
+
+
+def config_dict(name, wl, n_gpus, extra=None):
+    cfg = {
+        "workload": f"{name}: {wl['desc']}: {wl['N']} sensors, slide_win={wl['W']}, dim={wl['D']}, "
+                    f"topk={wl['K']}, {wl['B']} windows per GPU per step",
+        "sensors": wl["N"], "slide_win": wl["W"], "dim": wl["D"], "topk": wl["K"],
+        "windows_per_gpu": wl["B"], "global_batch": wl["B"] * n_gpus,
+        "parallelism": f"window-sharded dp{n_gpus}, flat fp32 gradient all-reduce (NCCL)" if n_gpus > 1 else "single GPU",
+        "step": "zero_grad+forward+mse+backward+Adam (train.py:68-73)",
+        "l2": "L2 flushed (256 MiB write) between timed iterations, outside the timed events",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_train_baseline(name, wl, budget_s, steps=None, warmup=1):
+    """The reference's CPU path (oracle port: same op sequence as models/GDN.py +
+    graph_layer.py, validated against the reference's files) on all host cores."""
+    import torch
+    from oracle import gdn_oracle as go
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    N, W, D, K, Bc = wl["N"], wl["W"], wl["D"], wl["K"], wl["cpu_B"]
+    sd = go.init_state(N, D, W, seed=5)
+    tr = go.OracleTrainer(sd, K)
+    g = torch.Generator().manual_seed(5)
+    x, y = torch.rand(Bc, N, W, generator=g), torch.rand(Bc, N, generator=g)
+    t0 = time.perf_counter()
+    for _ in range(max(warmup, 1)):
+        tr.train_step(x, y)
+    per = (time.perf_counter() - t0) / max(warmup, 1)
+    if steps is None:
+        steps = max(1, min(20, int(budget_s / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train_step(x, y)
+    dt = time.perf_counter() - t0
+    return {
+        "value": Bc * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{steps} train steps of {Bc} window(s) of {name} ({N} sensors) after {max(warmup, 1)} warm-up, "
+                  f"torch CPU fp32, {cores} threads",
+        "ms_per_step": 1e3 * dt / steps, "steps": steps,
+    }
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name, wl = args.workload, WORKLOADS[args.workload]
+    budget = 240.0
+    import torch  # noqa: F401
+    # one warm-up step tells us how many timed steps fit the budget
+    probe = cpu_train_baseline(name, wl, budget_s=1.0, steps=1, warmup=1)
+    per = probe["ms_per_step"] / 1e3
+    steps = max(1, min(args.steps, int(budget / max(per, 1e-6))))
+    warm = max(0, min(args.warmup, int(0.25 * budget / max(per, 1e-6))))
+    res = cpu_train_baseline(name, wl, budget_s=budget, steps=steps, warmup=max(warm, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(warm, 1), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(name, wl, args.gpus, {"cpu_windows_per_step": wl["cpu_B"]}),
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def profile_collect(lib):
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib.gdn_profile_collect(buf, len(buf))
+    rows = {}
+    for ln in buf.value.decode().splitlines():
+        nm, cnt, ms = ln.rsplit(" ", 2)
+        rows[nm] = (int(cnt), float(ms))
+    return n, rows
+
+
+def graphlayer_bytes(wl):
+    """algorithmic HBM bytes of GraphLayer fwd+bwd at the module boundary."""
+    N, W, D, K, B = wl["N"], wl["W"], wl["D"], wl["K"], wl["B"]
+    n = B * N
+    fwd = 4 * (n * W + N * D + n * D) + 4 * N * K + 4 * (D * W + 5 * D)
+    bwd = 4 * (n * D + n * W + 2 * N * D) + 4 * N * K + 8 * (D * W + 5 * D)
+    return fwd, bwd
+
+
+# --------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gdn_b200 import _lib, ops
+    from gdn_b200.dp import WindowShardedTrainer
+    from gdn_b200.models.GDN import GDN
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    name, wl = args.workload, WORKLOADS[args.workload]
+    N, W, D, K, B = wl["N"], wl["W"], wl["D"], wl["K"], wl["B"]
+
+    torch.manual_seed(5)                                   # run.sh seed; identical weights on every rank
+    model = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).to(dev)
+    model.train()
+    trainer = WindowShardedTrainer(model, lr=1e-3)
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)   # each rank: its own window shard
+    nbuf = 4
+    xs = [torch.rand(B, N, W, device=dev, generator=g) for _ in range(nbuf)]
+    ys = [torch.rand(B, N, device=dev, generator=g) for _ in range(nbuf)]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, flush_l2=True):
+        """per-step CUDA events on the current stream; the L2 flush sits between the events of
+        consecutive steps; returns the list of per-step milliseconds."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for i in range(steps):
+            if flush_l2:
+                flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            fn(i)
+            ev[i][1].record()
+        barrier()
+        return [a.elapsed_time(b) for a, b in ev]
+
+    def train_step(i):
+        return trainer.step(xs[i % nbuf], ys[i % nbuf])
+
+    for i in range(max(args.warmup, 3)):
+        train_step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(train_step, args.steps)
+    total_ms = sum(ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (total_ms / 1e3)
+
+    # ---- end to end: host buffers -> H2D -> step -> loss back on the host, every step
+    hx = [x.cpu().pin_memory() for x in xs]
+    hy = [y.cpu().pin_memory() for y in ys]
+    dx, dy = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+    losses = []
+
+    def e2e_step(i):
+        dx.copy_(hx[i % nbuf], non_blocking=True)
+        dy.copy_(hy[i % nbuf], non_blocking=True)
+        losses.append(trainer.step(dx, dy).item())           # D2H + sync, as train.py:76
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+           "h2d_bytes_per_step": int(xs[0].numel() * 4 + ys[0].numel() * 4), "d2h_bytes_per_step": 4,
+           "ms_per_step": e2e_ms / args.steps, "last_loss": losses[-1]}
+
+    # ---- per-kernel breakdown of the train step (separate, profiled steps)
+    lib.gdn_profile_enable(1)
+    PSTEPS = 3
+    for i in range(PSTEPS):
+        train_step(i)
+    torch.cuda.synchronize()
+    launches, rows = profile_collect(lib)
+    lib.gdn_profile_enable(0)
+    per_step_launches = launches // PSTEPS
+    kernels = {nm: {"launches_per_step": c / PSTEPS, "ms_per_step": t / PSTEPS} for nm, (c, t) in rows.items()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(name, wl, world),
+        "e2e": e2e, "gpu_launches": per_step_launches * args.steps,
+        "gpu_launches_per_step": per_step_launches,
+    }
+    if rank == 0:
+        line["clocks"] = clocks
+        line["kernels_ms_per_step"] = {k: round(v["ms_per_step"], 5) for k, v in sorted(
+            kernels.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+
+    if not args.no_extras and rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        # ---- GraphLayer fwd+bwd at the module boundary: the roofline the metric names
+        layer = model.gnn_layers[0].gnn
+        with torch.no_grad():
+            _, nbr = ops.graph_build(model.embedding.weight, K)
+        Vp = model.embedding.weight.detach().clone().requires_grad_(True)
+        gout = torch.rand(B * N, D, device=dev)
+        fwd_ms, bwd_ms = [], []
+        reps = max(5, min(args.steps, 20))
+        for i in range(reps + 3):
+            flush.fill_(i & 0xFF)
+            a, b_, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            out = layer.forward_batched(xs[i % nbuf], nbr, Vp)
+            b_.record()
+            out.backward(gout)
+            c.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                fwd_ms.append(a.elapsed_time(b_))
+                bwd_ms.append(b_.elapsed_time(c))
+            layer.zero_grad(set_to_none=True)
+            Vp.grad = None
+        fb, bb = graphlayer_bytes(wl)
+        f_ms, b_ms = statistics.mean(fwd_ms), statistics.mean(bwd_ms)
+        achieved = (fb + bb) / ((f_ms + b_ms) * 1e-3) / 1e9
+        line["roofline"] = {
+            "kernel": "GraphLayer fwd+bwd at the module boundary (gdn_graphlayer_fwd + gdn_graphlayer_bwd)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes": fb + bb,
+            "fwd_ms": f_ms, "bwd_ms": b_ms,
+            "fwd_frac": fb / (f_ms * 1e-3) / 1e9 / peak, "bwd_frac": bb / (b_ms * 1e-3) / 1e9 / peak,
+        }
+        # ---- score leg: eval forward + scoring of T ticks
+        model.eval()
+        T = 4096
+        with torch.no_grad():
+            ev_ms = []
+            for i in range(8):
+                flush.fill_(i)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                model(xs[i % nbuf], None)
+                b_.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ev_ms.append(a.elapsed_time(b_))
+            sc_pred = torch.rand(T, N, device=dev)
+            sc_gt = torch.rand(T, N, device=dev)
+            sc_ms = []
+            for i in range(6):
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ops.score(sc_pred, sc_gt)
+                b_.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    sc_ms.append(a.elapsed_time(b_))
+        model.train()
+        ev_wps = B / (statistics.mean(ev_ms) * 1e-3)
+        sc_wps = T / (statistics.mean(sc_ms) * 1e-3)
+        line["score"] = {"eval_forward_windows_per_s": ev_wps, "scoring_ticks_per_s": sc_wps,
+                         "score_windows_per_s": 1.0 / (1.0 / ev_wps + 1.0 / sc_wps), "scoring_T": T}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_train_baseline(name, wl, args.cpu_budget_s)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

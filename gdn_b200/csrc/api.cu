@@ -20,6 +20,37 @@ int cuda_fail(cudaError_t e, const char* what) {
     return (int)e > 0 ? (int)e : 1;
 }
 
+// ---------------------------------------------------------------------------------------
+// per-kernel profiler: events between launches, read back by gdn_profile_collect()
+// ---------------------------------------------------------------------------------------
+#define GDN_PROF_CAP 16384
+static bool g_prof_on = false;
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_ev[GDN_PROF_CAP];
+static const char* g_prof_name[GDN_PROF_CAP];
+static int g_prof_created = 0;
+static cudaStream_t g_prof_stream = nullptr;
+
+static void prof_push(const char* name) {
+    if (g_prof_n >= GDN_PROF_CAP) return;
+    if (g_prof_n >= g_prof_created) {
+        if (cudaEventCreate(&g_prof_ev[g_prof_created]) != cudaSuccess) return;
+        ++g_prof_created;
+    }
+    cudaEventRecord(g_prof_ev[g_prof_n], g_prof_stream);
+    g_prof_name[g_prof_n] = name;
+    ++g_prof_n;
+}
+
+void prof_enter(cudaStream_t st, const char* api) {
+    g_prof_stream = st;
+    if (g_prof_on) prof_push(api);      // names starting with '@' are API-entry markers
+}
+
+void prof_mark(const char* what) {
+    if (g_prof_on) prof_push(what);
+}
+
 int num_sms() {
     static int cached = 0;
     if (cached == 0) {
@@ -147,6 +178,48 @@ extern "C" {
 int gdn_version(void) { return GDN_B200_VERSION; }
 const char* gdn_last_error(void) { return g_err; }
 
+// ------------------------------------------------------------------------------- profiler
+int gdn_profile_enable(int on) {
+    g_prof_on = on != 0;
+    g_prof_n = 0;
+    return 0;
+}
+
+// Synchronises on the last recorded event and writes one line per kernel name:
+// "<name> <launches> <total_ms>\n" (time from the previous event on the stream to the event
+// recorded after the launch).  Returns the number of launches recorded, <0 on error.
+int gdn_profile_collect(char* buf, size_t buf_bytes) {
+    if (buf == nullptr || buf_bytes == 0) { set_error("profile_collect: NULL buffer"); return -1; }
+    buf[0] = 0;
+    if (g_prof_n == 0) return 0;
+    cudaError_t e = cudaEventSynchronize(g_prof_ev[g_prof_n - 1]);
+    if (e != cudaSuccess) { cuda_fail(e, "profile_collect"); return -1; }
+    const int MAXN = 64;
+    const char* names[MAXN];
+    int counts[MAXN];
+    double totals[MAXN];
+    int nn = 0, launches = 0;
+    for (int i = 0; i < g_prof_n; ++i) {
+        if (g_prof_name[i][0] == '@') continue;
+        float ms = 0.f;
+        if (i == 0 || cudaEventElapsedTime(&ms, g_prof_ev[i - 1], g_prof_ev[i]) != cudaSuccess) continue;
+        int k = 0;
+        for (; k < nn; ++k) if (strcmp(names[k], g_prof_name[i]) == 0) break;
+        if (k == nn) { if (nn == MAXN) continue; names[nn] = g_prof_name[i]; counts[nn] = 0; totals[nn] = 0.0; ++nn; }
+        counts[k] += 1;
+        totals[k] += (double)ms;
+        ++launches;
+    }
+    size_t off = 0;
+    for (int k = 0; k < nn; ++k) {
+        int w = snprintf(buf + off, buf_bytes - off, "%s %d %.6f\n", names[k], counts[k], totals[k]);
+        if (w < 0 || (size_t)w >= buf_bytes - off) break;
+        off += (size_t)w;
+    }
+    g_prof_n = 0;
+    return launches;
+}
+
 // ------------------------------------------------------------------------------- graph
 size_t gdn_graph_build_ws_bytes(int N, int D, int K) { return graph_build_ws_bytes(N, D, K); }
 
@@ -154,6 +227,7 @@ int gdn_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* 
                     int use_tensor_cores, void* stream) {
     GDN_CHECK_ARG(V != nullptr, "V is NULL");
     GDN_CHECK_ARG(N >= 1 && D >= 1 && K >= 1 && K <= N, "graph_build: bad shape N=%d D=%d K=%d", N, D, K);
+    prof_enter((cudaStream_t)stream, "@graph_build");
     return launch_graph_build(V, N, D, K, idx, nbr, ws, ws_bytes, use_tensor_cores, (cudaStream_t)stream);
 }
 
@@ -179,6 +253,7 @@ int gdn_graphlayer_fwd(const gdn_dims* d, const float* x, const float* V, const 
     cudaStream_t st = (cudaStream_t)stream;
     char* ctx = (char*)ctx_;
     (void)ws; (void)ws_bytes;
+    prof_enter(st, "@graphlayer_fwd");
     if (int rc = launch_prep(s, x, V, p, ctx, L, st)) return rc;
     if (int rc = launch_attn_fwd(s, nbr, ctx, L, alpha, st)) return rc;
     return launch_lin_fwd(s, (const float*)(ctx + L.A), p, out, st);
@@ -202,6 +277,7 @@ int gdn_graphlayer_bwd(const gdn_dims* d, const float* g_out, const float* V, co
     float* gA = (float*)(ws + WL.gA);
     double* part = (double*)(ws + WL.part);
     int nrec = 0, nrec_u = 0, nrec_e = 0;
+    prof_enter(st, "@graphlayer_bwd");
     if (int rc = launch_lin_bwd(s, g_out, (const float*)(ctx + L.A), p, gA, part, &nrec, st)) return rc;
     if (int rc = launch_attn_bwd(s, nbr, ctx, L, gA, (float*)(ws + WL.gsiT), (float*)(ws + WL.gsjT), sm.gev,
                                  sm.part_u, &nrec_u, st)) return rc;
@@ -239,6 +315,7 @@ int gdn_fused_fwd(const gdn_dims* d, const float* x, const float* V, const int32
     char* ws = (char*)ws_;
     float* bnc = (float*)(ctx + L.bn);
     double* part = (double*)(ws + WL.part);
+    prof_enter(st, "@fused_fwd");
     if (int rc = launch_prep(s, x, V, p, ctx, L, st)) return rc;
     if (int rc = launch_attn_fwd(s, nbr, ctx, L, nullptr, st)) return rc;
     const HeadArgs ha = head_args(s, ctx, L, V, p, h, dp, training);
@@ -279,6 +356,7 @@ int gdn_fused_bwd(const gdn_dims* d, const float* g_pred, const float* V, const 
     ba.gV = s.S > 1 ? (float*)(ws + WL.gV) : g->embedding;
     ba.gA = (float*)(ws + WL.gA);
     int nrec = 0, nrec_u = 0, nrec_e = 0;
+    prof_enter(st, "@fused_bwd");
     if (int rc = launch_bwd1(s, ha, ba, part, gh, sm.c2, st)) return rc;
     if (int rc = launch_bwd2(s, ha, ba, part, gh, sm.c1, g->embedding, st)) return rc;
     if (int rc = launch_bwd3(s, ha, ba, part, &nrec, st)) return rc;
@@ -295,6 +373,7 @@ int gdn_ctx_alpha(const gdn_dims* d, const int32_t* nbr, const void* ctx_, float
     GDN_CHECK_ARG(nbr && ctx_ && alpha, "ctx_alpha: NULL argument");
     // the attention part of the ctx layout does not depend on the fused flag
     const CtxLayout L = ctx_layout(s, false);
+    prof_enter((cudaStream_t)stream, "@ctx_alpha");
     return launch_attn_alpha(s, nbr, (const char*)ctx_, L, alpha, (cudaStream_t)stream);
 }
 
@@ -306,6 +385,7 @@ int gdn_score(const float* pred, const float* gt, int T, int N, double* scores, 
     GDN_CHECK_ARG(pred && gt, "score: NULL input");
     GDN_CHECK_ARG(T >= 1 && N >= 1, "score: bad shape T=%d N=%d", T, N);
     GDN_CHECK_ARG(ws != nullptr && ws_bytes >= score_ws_bytes(T, N), "score: workspace too small");
+    prof_enter((cudaStream_t)stream, "@score");
     return launch_score(pred, gt, T, N, scores, top1, stats, ws, ws_bytes, (cudaStream_t)stream);
 }
 

@@ -27,7 +27,12 @@ int  cuda_fail(cudaError_t e, const char* what);
     do {                                                         \
         cudaError_t e__ = cudaGetLastError();                    \
         if (e__ != cudaSuccess) return gdn::cuda_fail(e__, what); \
+        gdn::prof_mark(what);                                    \
     } while (0)
+
+// optional per-kernel timing (gdn_profile_enable): an event is recorded after every launch
+void prof_enter(cudaStream_t st, const char* api);
+void prof_mark(const char* what);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int    ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -106,6 +106,12 @@ typedef struct gdn_dropout {
 int         gdn_version(void);
 const char* gdn_last_error(void);
 
+/* ---- measurement hook (bench.py): when enabled, a CUDA event is recorded on the call's
+ * stream after every kernel launch; gdn_profile_collect() synchronises and writes one text
+ * line per kernel "<name> <launches> <total_ms>" and returns the number of launches. */
+int gdn_profile_enable(int on);
+int gdn_profile_collect(char* buf, size_t buf_bytes);
+
 /* ---- a1: learned graph (models/GDN.py:143-159) ---------------------------------------
  * V [N, D] -> idx [N, K] int64 (torch.topk order: descending cosine, ties -> lower index)
  *          and nbr [N, K+1] int32: the neighbour list GraphLayer actually uses after
