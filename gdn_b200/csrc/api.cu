@@ -131,6 +131,7 @@ WsLayout ws_layout(const Shape& s, bool fused) {
     L.gV = take(&off, (fused && s.S > 1) ? (size_t)s.S * s.N * s.D * sizeof(float) : 0);
     // small: c2[2D] c1[2D] gev[2N] part_u[2*sms*64] part_e[2*sms*2D]   (floats)
     L.small = take(&off, ((size_t)4 * s.D + 2 * s.N + (size_t)2 * num_sms() * (64 + 2 * s.D)) * sizeof(float));
+    L.sums = take(&off, (rec + 64) * sizeof(double));
     L.total = off;
     return L;
 }
@@ -281,9 +282,10 @@ int gdn_graphlayer_bwd(const gdn_dims* d, const float* g_out, const float* V, co
     if (int rc = launch_lin_bwd(s, g_out, (const float*)(ctx + L.A), p, gA, part, &nrec, st)) return rc;
     if (int rc = launch_attn_bwd(s, nbr, ctx, L, gA, (float*)(ws + WL.gsiT), (float*)(ws + WL.gsjT), sm.gev,
                                  sm.part_u, &nrec_u, st)) return rc;
-    if (int rc = launch_fin_layer(s, part, nrec, sm.part_u, nrec_u, p, g, st)) return rc;
+    double* sums = (double*)(ws + WL.sums);
+    if (int rc = launch_fin_layer(s, part, nrec, sm.part_u, nrec_u, sums, p, g, st)) return rc;
     if (int rc = launch_embed_grads(s, V, sm.gev, p, 0, g->embedding, sm.part_e, &nrec_e, st)) return rc;
-    return launch_fin_embed(s, sm.part_e, nrec_e, g, st);
+    return launch_fin_embed(s, sm.part_e, nrec_e, sums, g, st);
 }
 
 // ------------------------------------------------------------------------------- fused GDN
@@ -322,8 +324,9 @@ int gdn_fused_fwd(const gdn_dims* d, const float* x, const float* V, const int32
     if (training) {
         int nrec = 0;
         if (int rc = launch_moments(s, ha.A, part, &nrec, st)) return rc;
-        if (int rc = launch_fin_bn1(s, part, nrec, p, bnc, &h->bn1, st)) return rc;
-        if (int rc = launch_fwd_stats2(s, ha, part, &h->bn2, bnc, st)) return rc;
+        double* sums = (double*)(ws + WL.sums);
+        if (int rc = launch_fin_bn1(s, part, nrec, sums, p, bnc, &h->bn1, st)) return rc;
+        if (int rc = launch_fwd_stats2(s, ha, part, sums, &h->bn2, bnc, st)) return rc;
     } else {
         if (int rc = launch_fin_bn_eval(s, p, h, bnc, st)) return rc;
     }
@@ -357,14 +360,15 @@ int gdn_fused_bwd(const gdn_dims* d, const float* g_pred, const float* V, const 
     ba.gA = (float*)(ws + WL.gA);
     int nrec = 0, nrec_u = 0, nrec_e = 0;
     prof_enter(st, "@fused_bwd");
-    if (int rc = launch_bwd1(s, ha, ba, part, gh, sm.c2, st)) return rc;
-    if (int rc = launch_bwd2(s, ha, ba, part, gh, sm.c1, g->embedding, st)) return rc;
+    double* sums = (double*)(ws + WL.sums);
+    if (int rc = launch_bwd1(s, ha, ba, part, sums, gh, sm.c2, st)) return rc;
+    if (int rc = launch_bwd2(s, ha, ba, part, sums, gh, sm.c1, g->embedding, st)) return rc;
     if (int rc = launch_bwd3(s, ha, ba, part, &nrec, st)) return rc;
     if (int rc = launch_attn_bwd(s, nbr, ctx, L, ba.gA, (float*)(ws + WL.gsiT), (float*)(ws + WL.gsjT), sm.gev,
                                  sm.part_u, &nrec_u, st)) return rc;
-    if (int rc = launch_fin_layer(s, part, nrec, sm.part_u, nrec_u, p, g, st)) return rc;
+    if (int rc = launch_fin_layer(s, part, nrec, sm.part_u, nrec_u, sums, p, g, st)) return rc;
     if (int rc = launch_embed_grads(s, V, sm.gev, p, 1, g->embedding, sm.part_e, &nrec_e, st)) return rc;
-    return launch_fin_embed(s, sm.part_e, nrec_e, g, st);
+    return launch_fin_embed(s, sm.part_e, nrec_e, sums, g, st);
 }
 
 int gdn_ctx_alpha(const gdn_dims* d, const int32_t* nbr, const void* ctx_, float* alpha, void* stream) {

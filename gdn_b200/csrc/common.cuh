@@ -77,7 +77,8 @@ struct WsLayout {
     size_t part;     // per-CTA partial sums (doubles), size part_bytes
     size_t part_bytes;
     size_t gV;       // [S][N][D] partial embedding gradients (S > 1)
-    size_t small;    // doubles: reduced sums
+    size_t small;    // floats: coefficient vectors, small partials
+    size_t sums;     // doubles: one reduced record (+ the 64 attention-scalar sums)
     size_t total;
 };
 WsLayout ws_layout(const Shape& s, bool fused);

@@ -650,7 +650,35 @@ k_bwd3(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 }
 
 // ---------------------------------------------------------------------------------------
-// finalize kernels (one CTA, 256 threads)
+// per-CTA partial records -> one record of doubles (fixed summation order: deterministic)
+// block (32, 8): x <-> entry, y strides the records; grid = ceil(rec / 32)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_reduce_part(const T* __restrict__ part, int nrec, int rec, double* __restrict__ sums) {
+    __shared__ double sh[8][33];
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (e < rec)
+        for (int q = threadIdx.y; q < nrec; q += 8) s += (double)part[(size_t)q * rec + e];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < rec) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+        sums[e] = t;
+    }
+}
+
+template <typename T>
+static int reduce_part(const T* part, int nrec, int rec, double* sums, cudaStream_t st) {
+    k_reduce_part<T><<<(rec + 31) / 32, dim3(32, 8), 0, st>>>(part, nrec, rec, sums);
+    GDN_CHECK_LAUNCH("k_reduce_part");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// finalize kernels (one CTA, 256 threads; they read ONE pre-reduced record)
 // ---------------------------------------------------------------------------------------
 // BN1 statistics from the moments of A; writes ctx.bn[0..3], updates running stats.
 __global__ void k_fin_bn1(const double* __restrict__ part, int nrec, long long n, int W, int D,
@@ -776,7 +804,7 @@ __global__ void k_reduce_gV(const float* __restrict__ gVp, int S, long long ND, 
 //   g_Wl[d,w] = main[d,w] + a_i[d] g_ui[w] + a_j[d] g_uj[w];  g_bias = main
 //   g_a_i[d] = sum_w Wl[d,w] g_ui[w];  g_a_j likewise
 __global__ void k_fin_layer(const double* __restrict__ part, int nrec,
-                            const float* __restrict__ part_u, int nrec_u, int W, int D,
+                            const double* __restrict__ part_u, int nrec_u, int W, int D,
                             const float* __restrict__ Wl, const float* __restrict__ a_i, const float* __restrict__ a_j,
                             float* __restrict__ g_Wl, float* __restrict__ g_bias,
                             float* __restrict__ g_ai, float* __restrict__ g_aj) {
@@ -811,7 +839,7 @@ __global__ void k_fin_layer(const double* __restrict__ part, int nrec,
     }
 }
 
-__global__ void k_fin_embed(const float* __restrict__ part, int nrec, int D,
+__global__ void k_fin_embed(const double* __restrict__ part, int nrec, int D,
                             float* __restrict__ g_aei, float* __restrict__ g_aej) {
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         double si = 0.0, sj = 0.0;
@@ -876,10 +904,11 @@ int launch_moments(const Shape& s, const float* A, double* part, int* nrec, cuda
     return 0;
 }
 
-int launch_fin_bn1(const Shape& s, const double* part, int nrec, const gdn_layer_params* p, float* bnc,
+int launch_fin_bn1(const Shape& s, const double* part, int nrec, double* sums, const gdn_layer_params* p, float* bnc,
                    const gdn_bn* bn, cudaStream_t st) {
     const size_t smem = ((size_t)s.W * s.W + s.W) * sizeof(double);
-    k_fin_bn1<<<1, 256, smem, st>>>(part, nrec, s.n, s.W, s.D, p->lin_weight, p->bias, bnc,
+    if (int rc = reduce_part<double>(part, nrec, s.W * s.W + s.W, sums, st)) return rc;
+    k_fin_bn1<<<1, 256, smem, st>>>(sums, 1, s.n, s.W, s.D, p->lin_weight, p->bias, bnc,
                                     bn->running_mean, bn->running_var, (long long*)bn->num_batches_tracked);
     GDN_CHECK_LAUNCH("k_fin_bn1");
     return 0;
@@ -895,7 +924,7 @@ int launch_fin_bn_eval(const Shape& s, const gdn_layer_params* p, const gdn_head
 
 static size_t dsm_bytes(int nv) { return (size_t)8 * nv * 32 * sizeof(double); }
 
-int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, const gdn_bn* bn, float* bnc,
+int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, double* sums, const gdn_bn* bn, float* bnc,
                       cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
 #define CALL(DPLC, WPC)                                                                                   \
@@ -908,7 +937,8 @@ int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, const gdn
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_fwd_stats2");
-    k_fin_bn2<<<1, 256, 0, st>>>(part, grid, s.n, s.D, bnc, bn->running_mean, bn->running_var,
+    if (int rc = reduce_part<double>(part, grid, 2 * s.D, sums, st)) return rc;
+    k_fin_bn2<<<1, 256, 0, st>>>(sums, 1, s.n, s.D, bnc, bn->running_mean, bn->running_var,
                                  (long long*)bn->num_batches_tracked);
     GDN_CHECK_LAUNCH("k_fin_bn2");
     return 0;
@@ -923,7 +953,7 @@ int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t 
     return 0;
 }
 
-int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, gdn_head_grads* gh,
+int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
                 float* c2, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
 #define CALL(DPLC, WPC)                                                                                 \
@@ -936,12 +966,13 @@ int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd1");
-    k_fin_bwd1<<<1, 256, 0, st>>>(part, grid, s.n, s.D, gh->out_w, gh->bn2_weight, gh->bn2_bias, gh->out_b, c2);
+    if (int rc = reduce_part<double>(part, grid, 3 * s.D + 32, sums, st)) return rc;
+    k_fin_bwd1<<<1, 256, 0, st>>>(sums, 1, s.n, s.D, gh->out_w, gh->bn2_weight, gh->bn2_bias, gh->out_b, c2);
     GDN_CHECK_LAUNCH("k_fin_bwd1");
     return 0;
 }
 
-int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, gdn_head_grads* gh,
+int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
                 float* c1, float* gV_final, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
 #define CALL(DPLC, WPC)                                                                                 \
@@ -954,7 +985,8 @@ int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd2");
-    k_fin_bwd2<<<1, 256, 0, st>>>(part, grid, s.n, s.D, gh->bn1_weight, gh->bn1_bias, c1);
+    if (int rc = reduce_part<double>(part, grid, 2 * s.D, sums, st)) return rc;
+    k_fin_bwd2<<<1, 256, 0, st>>>(sums, 1, s.n, s.D, gh->bn1_weight, gh->bn1_bias, c1);
     GDN_CHECK_LAUNCH("k_fin_bwd2");
     if (s.S > 1) {
         const long long ND = (long long)s.N * s.D;
@@ -976,16 +1008,20 @@ int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
     return 0;
 }
 
-int launch_fin_layer(const Shape& s, const double* part, int nrec, const float* part_u, int nrec_u,
+int launch_fin_layer(const Shape& s, const double* part, int nrec, const float* part_u, int nrec_u, double* sums,
                      const gdn_layer_params* p, gdn_layer_grads* g, cudaStream_t st) {
-    k_fin_layer<<<1, 256, 0, st>>>(part, nrec, part_u, nrec_u, s.W, s.D, p->lin_weight, p->att_i, p->att_j,
+    const int rec = s.D * s.W + s.D;
+    if (int rc = reduce_part<double>(part, nrec, rec, sums, st)) return rc;
+    if (int rc = reduce_part<float>(part_u, nrec_u, 64, sums + rec, st)) return rc;
+    k_fin_layer<<<1, 256, 0, st>>>(sums, 1, sums + rec, 1, s.W, s.D, p->lin_weight, p->att_i, p->att_j,
                                    g->lin_weight, g->bias, g->att_i, g->att_j);
     GDN_CHECK_LAUNCH("k_fin_layer");
     return 0;
 }
 
-int launch_fin_embed(const Shape& s, const float* part, int nrec, gdn_layer_grads* g, cudaStream_t st) {
-    k_fin_embed<<<1, 256, 0, st>>>(part, nrec, s.D, g->att_em_i, g->att_em_j);
+int launch_fin_embed(const Shape& s, const float* part, int nrec, double* sums, gdn_layer_grads* g, cudaStream_t st) {
+    if (int rc = reduce_part<float>(part, nrec, 2 * s.D, sums, st)) return rc;
+    k_fin_embed<<<1, 256, 0, st>>>(sums, 1, s.D, g->att_em_i, g->att_em_j);
     GDN_CHECK_LAUNCH("k_fin_embed");
     return 0;
 }

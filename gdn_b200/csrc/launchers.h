@@ -44,20 +44,21 @@ int launch_lin_fwd(const Shape& s, const float* A, const gdn_layer_params* p, fl
 int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_layer_params* p, float* gA,
                    double* part, int* nrec, cudaStream_t st);
 int launch_moments(const Shape& s, const float* A, double* part, int* nrec, cudaStream_t st);
-int launch_fin_bn1(const Shape& s, const double* part, int nrec, const gdn_layer_params* p, float* bnc,
+int launch_fin_bn1(const Shape& s, const double* part, int nrec, double* sums, const gdn_layer_params* p, float* bnc,
                    const gdn_bn* bn, cudaStream_t st);
 int launch_fin_bn_eval(const Shape& s, const gdn_layer_params* p, const gdn_head_params* h, float* bnc,
                        cudaStream_t st);
-int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, const gdn_bn* bn, float* bnc, cudaStream_t st);
+int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, double* sums, const gdn_bn* bn, float* bnc,
+                      cudaStream_t st);
 int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t st);
-int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, gdn_head_grads* gh, float* c2,
-                cudaStream_t st);
-int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, gdn_head_grads* gh, float* c1,
-                float* gV_final, cudaStream_t st);
+int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
+                float* c2, cudaStream_t st);
+int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
+                float* c1, float* gV_final, cudaStream_t st);
 int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st);
-int launch_fin_layer(const Shape& s, const double* part, int nrec, const float* part_u, int nrec_u,
+int launch_fin_layer(const Shape& s, const double* part, int nrec, const float* part_u, int nrec_u, double* sums,
                      const gdn_layer_params* p, gdn_layer_grads* g, cudaStream_t st);
-int launch_fin_embed(const Shape& s, const float* part, int nrec, gdn_layer_grads* g, cudaStream_t st);
+int launch_fin_embed(const Shape& s, const float* part, int nrec, double* sums, gdn_layer_grads* g, cudaStream_t st);
 
 // graph_build.cu
 size_t graph_build_ws_bytes(int N, int D, int K);

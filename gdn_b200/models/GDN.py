@@ -132,13 +132,16 @@ class GDN(nn.Module):
         self._dropout_mask = mask
 
     def build_graph(self):
-        """models/GDN.py:143-159; cached on the embedding's version counter (it only changes when
-        the optimiser steps or a checkpoint is loaded)."""
+        """models/GDN.py:143-159.  The reference rebuilds the graph in every forward; so do we in
+        training mode (fused optimisers update the embedding without bumping its version counter,
+        so no cache key is trustworthy there).  In eval mode the graph is reused while the embedding
+        storage and version are unchanged and no training forward has run in between."""
         w = self.embedding.weight
         key = (w.data_ptr(), w._version, int(self.topk), int(self.use_tensor_cores), str(w.device))
-        if self._graph_cache is None or self._graph_cache[0] != key:
+        if self.training or self._graph_cache is None or self._graph_cache[0] != key:
             idx, nbr = ops.graph_build(w, self.topk, use_tensor_cores=self.use_tensor_cores)
-            self._graph_cache = (key, idx, nbr)
+            self._graph_cache = None if self.training else (key, idx, nbr)
+            return idx, nbr
         return self._graph_cache[1], self._graph_cache[2]
 
     def forward(self, data, org_edge_index=None):
