@@ -79,6 +79,8 @@ int make_shape(const gdn_dims* d, Shape* s, bool need_dwide) {
     s->n = (long long)d->B * d->N;
     s->WP = d->W <= 8 ? 8 : (d->W <= 16 ? 16 : 32);
     s->DPL = d->D / 32;
+    GDN_CHECK_ARG((long long)d->N * s->Bs * s->WP < (1ll << 31), "N*B*W = %lld elements exceed the 32-bit gather offsets",
+                  (long long)d->N * s->Bs * s->WP);
     // sensor-major passes: tasks = N * S; aim for >= 8 tasks per resident warp slot
     const long long want = (long long)num_sms() * 8 * 4;
     int S = (int)((want + d->N - 1) / d->N);
@@ -101,7 +103,7 @@ CtxLayout ctx_layout(const Shape& s, bool fused) {
     CtxLayout L;
     size_t off = 0;
     const size_t nb = (size_t)s.N * s.Bs * sizeof(float);
-    L.xT = take(&off, nb * s.W);
+    L.xT = take(&off, nb * s.WP);
     L.siT = take(&off, nb);
     L.sjT = take(&off, nb);
     L.mT = take(&off, nb);

@@ -10,7 +10,7 @@
 //     D-wide transform Wl.A commutes with the aggregation and runs afterwards).
 //
 // Layout: the graph is identical for every window, so a warp owns one target sensor i and
-// 32 windows (lane <-> b).  x is first transposed to xT[N][W][Bs] (window index fastest):
+// 32 windows (lane <-> b).  x is first transposed to xT[N][Bs/32][WP][32] (window index fastest):
 // every gather of a neighbour is then one fully used 128-byte line per (source, w), the
 // neighbour index is warp-uniform, and the backward's scatter into g_sj is one coalesced
 // RED per edge instead of 32 scattered atomics.
@@ -52,10 +52,12 @@ __global__ void k_node_scalars(const float* __restrict__ V, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------
-// x[B][N][W] -> xT[N][W][Bs], s_iT[N][Bs], s_jT[N][Bs]   (zero padded for b >= B)
+// x[B][N][W] -> xT[N][C][WP][32] (C = Bs/32 window chunks, w padded with zeros to WP),
+// s_iT[N][Bs], s_jT[N][Bs]   (zero padded for b >= B)
+// A lane's 16 gathers of one neighbour are then base + w*32: immediate offsets, no address math.
 // ---------------------------------------------------------------------------------------
 __global__ void k_transpose_scalars(const float* __restrict__ x, const float* __restrict__ uv,
-                                    const float* __restrict__ ev, int B, int N, int W, int Bs,
+                                    const float* __restrict__ ev, int B, int N, int W, int WP, int Bs,
                                     float* __restrict__ xT, float* __restrict__ siT, float* __restrict__ sjT) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -63,16 +65,19 @@ __global__ void k_transpose_scalars(const float* __restrict__ x, const float* __
     const int chunks = Bs >> 5;
     const long long tasks = (long long)N * chunks;
     for (long long t = warp; t < tasks; t += nwarps) {
-        const int i = (int)(t / chunks);
-        const int b = (int)(t % chunks) * 32 + lane;
+        const int i = (int)(t / chunks), c = (int)(t % chunks);
+        const int b = c * 32 + lane;
         float si = 0.f, sj = 0.f;
         const bool ok = b < B;
         const float* row = x + ((size_t)b * N + i) * W;
-        for (int w = 0; w < W; ++w) {
-            const float v = ok ? __ldg(row + w) : 0.f;
-            xT[((size_t)i * W + w) * Bs + b] = v;
-            si = fmaf(v, uv[w], si);
-            sj = fmaf(v, uv[32 + w], sj);
+        float* dst = xT + ((size_t)i * chunks + c) * WP * 32 + lane;
+        for (int w = 0; w < WP; ++w) {
+            const float v = (ok && w < W) ? __ldg(row + w) : 0.f;
+            dst[w * 32] = v;
+            if (w < W) {
+                si = fmaf(v, uv[w], si);
+                sj = fmaf(v, uv[32 + w], sj);
+            }
         }
         siT[(size_t)i * Bs + b] = ok ? si + ev[i] : 0.f;
         sjT[(size_t)i * Bs + b] = ok ? sj + ev[N + i] : 0.f;
@@ -81,6 +86,8 @@ __global__ void k_transpose_scalars(const float* __restrict__ x, const float* __
 
 // ---------------------------------------------------------------------------------------
 // forward: A, segment max m, 1/(segment sum + 1e-16); optional alpha
+// tasks are chunk-major (all sensors of window chunk 0, then chunk 1, ...) so that the
+// gather working set at any time is one chunk of xT (N*WP*128 bytes)
 // ---------------------------------------------------------------------------------------
 template <int WP>
 __global__ void __launch_bounds__(256)
@@ -93,31 +100,34 @@ k_attn_fwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int chunks = Bs >> 5;
     const long long tasks = (long long)N * chunks;
+    const unsigned xstride = (unsigned)chunks * WP * 32;
     for (long long t = warp; t < tasks; t += nwarps) {
-        const int i = (int)(t / chunks);
-        const int b = (int)(t % chunks) * 32 + lane;
+        const int c = (int)(t / N), i = (int)(t % N);
+        const int b = c * 32 + lane;
         const int32_t* nb = nbr + (size_t)i * Kp;
+        const float* sjb = sjT + b;
+        const float* xb = xT + (size_t)c * WP * 32 + lane;
         const float si = siT[(size_t)i * Bs + b];
         float m = -INFINITY;
+        int deg = 0;
         for (int k = 0; k < Kp; ++k) {
             const int src = __ldg(nb + k);
             if (src < 0) break;
-            m = fmaxf(m, leaky(si + sjT[(size_t)src * Bs + b]));
+            ++deg;
+            m = fmaxf(m, leaky(si + sjb[(unsigned)src * (unsigned)Bs]));
         }
         float acc[WP];
 #pragma unroll
         for (int w = 0; w < WP; ++w) acc[w] = 0.f;
         float sum = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < Kp; ++k) {
-            const int src = __ldg(nb + k);
-            if (src < 0) break;
-            const float p = __expf(leaky(si + sjT[(size_t)src * Bs + b]) - m);
+#pragma unroll 4
+        for (int k = 0; k < deg; ++k) {
+            const unsigned src = (unsigned)__ldg(nb + k);
+            const float p = expf(leaky(si + sjb[src * (unsigned)Bs]) - m);
             sum += p;
-            const float* xs = xT + (size_t)src * W * Bs + b;
+            const float* xs = xb + src * xstride;
 #pragma unroll
-            for (int w = 0; w < WP; ++w)
-                if (w < W) acc[w] = fmaf(p, xs[(size_t)w * Bs], acc[w]);
+            for (int w = 0; w < WP; ++w) acc[w] = fmaf(p, xs[w * 32], acc[w]);
         }
         const float linv = 1.f / (sum + GDN_SOFTMAX_EPS);
         mT[(size_t)i * Bs + b] = m;
@@ -139,7 +149,7 @@ k_attn_fwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
                 float* al = alpha + ((size_t)b * N + i) * Kp;
                 for (int k = 0; k < Kp; ++k) {
                     const int src = __ldg(nb + k);
-                    al[k] = src < 0 ? 0.f : __expf(leaky(si + sjT[(size_t)src * Bs + b]) - m) * linv;
+                    al[k] = src < 0 ? 0.f : expf(leaky(si + sjb[(unsigned)src * (unsigned)Bs]) - m) * linv;
                 }
             }
         }
@@ -166,7 +176,7 @@ __global__ void k_attn_alpha(const float* __restrict__ siT, const float* __restr
         float* al = alpha + ((size_t)b * N + i) * Kp;
         for (int k = 0; k < Kp; ++k) {
             const int src = __ldg(nb + k);
-            al[k] = src < 0 ? 0.f : __expf(leaky(si + sjT[(size_t)src * Bs + b]) - m) * linv;
+            al[k] = src < 0 ? 0.f : expf(leaky(si + sjT[(size_t)src * Bs + b]) - m) * linv;
         }
     }
 }
@@ -190,41 +200,52 @@ k_attn_bwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int chunks = Bs >> 5;
     const long long tasks = (long long)N * chunks;
+    const unsigned xstride = (unsigned)chunks * WP * 32;
     for (long long t = warp; t < tasks; t += nwarps) {
-        const int i = (int)(t / chunks);
-        const int b = (int)(t % chunks) * 32 + lane;
+        const int c = (int)(t / N), i = (int)(t % N);
+        const int b = c * 32 + lane;
         const bool ok = b < B;
         const int32_t* nb = nbr + (size_t)i * Kp;
+        const float* sjb = sjT + b;
+        float* gsjb = gsjT + b;
+        const float* xb = xT + (size_t)c * WP * 32 + lane;
         const float si = siT[(size_t)i * Bs + b];
         const float m = mT[(size_t)i * Bs + b], linv = linvT[(size_t)i * Bs + b];
         float g[WP];
         const float* grow = gA + ((size_t)(ok ? b : 0) * N + i) * W;
 #pragma unroll
         for (int w = 0; w < WP; ++w) g[w] = (ok && w < W) ? grow[w] : 0.f;
-        float dot = 0.f;
-#pragma unroll 2
+        int deg = 0;
         for (int k = 0; k < Kp; ++k) {
-            const int src = __ldg(nb + k);
-            if (src < 0) break;
-            const float a = __expf(leaky(si + sjT[(size_t)src * Bs + b]) - m) * linv;
-            const float* xs = xT + (size_t)src * W * Bs + b;
-            float ga = 0.f;
+            if (__ldg(nb + k) < 0) break;
+            ++deg;
+        }
+        float dot = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < deg; ++k) {
+            const unsigned src = (unsigned)__ldg(nb + k);
+            const float a = expf(leaky(si + sjb[src * (unsigned)Bs]) - m) * linv;
+            const float* xs = xb + src * xstride;
+            float ga0 = 0.f, ga1 = 0.f;
 #pragma unroll
-            for (int w = 0; w < WP; ++w)
-                if (w < W) ga = fmaf(g[w], xs[(size_t)w * Bs], ga);
+            for (int w = 0; w < WP; w += 2) {
+                ga0 = fmaf(g[w], xs[w * 32], ga0);
+                ga1 = fmaf(g[w + 1], xs[(w + 1) * 32], ga1);
+            }
+            const float ga = ga0 + ga1;
             stash[k * 32] = ga;
             dot = fmaf(a, ga, dot);
         }
         float gsi = 0.f;
-        for (int k = 0; k < Kp; ++k) {
-            const int src = __ldg(nb + k);
-            if (src < 0) break;
-            const float pre = si + sjT[(size_t)src * Bs + b];
-            const float a = __expf(leaky(pre) - m) * linv;
+#pragma unroll 2
+        for (int k = 0; k < deg; ++k) {
+            const unsigned src = (unsigned)__ldg(nb + k);
+            const float pre = si + sjb[src * (unsigned)Bs];
+            const float a = expf(leaky(pre) - m) * linv;
             const float gl = a * (stash[k * 32] - dot);
             const float gp = pre > 0.f ? gl : GDN_NEG_SLOPE * gl;
             gsi += gp;
-            if (ok) atomicAdd(gsjT + (size_t)src * Bs + b, gp);
+            if (ok) atomicAdd(gsjb + src * (unsigned)Bs, gp);
         }
         gsiT[(size_t)i * Bs + b] = ok ? gsi : 0.f;
     }
@@ -242,23 +263,24 @@ k_scalar_grads(const float* __restrict__ xT, const float* __restrict__ gsiT, con
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int chunks = Bs >> 5;
     float aui[WP], auj[WP];
 #pragma unroll
     for (int w = 0; w < WP; ++w) aui[w] = auj[w] = 0.f;
     for (int i = warp; i < N; i += nwarps) {
         float ssi = 0.f, ssj = 0.f;
-        for (int b = lane; b < Bs; b += 32) {
+        for (int c = 0; c < chunks; ++c) {
+            const int b = c * 32 + lane;
             const float gi = gsiT[(size_t)i * Bs + b], gj = gsjT[(size_t)i * Bs + b];
             ssi += gi;
             ssj += gj;
-            const float* xs = xT + (size_t)i * W * Bs + b;
+            const float* xs = xT + ((size_t)i * chunks + c) * WP * 32 + lane;
 #pragma unroll
-            for (int w = 0; w < WP; ++w)
-                if (w < W) {
-                    const float xv = xs[(size_t)w * Bs];
-                    aui[w] = fmaf(gi, xv, aui[w]);
-                    auj[w] = fmaf(gj, xv, auj[w]);
-                }
+            for (int w = 0; w < WP; ++w) {
+                const float xv = xs[w * 32];
+                aui[w] = fmaf(gi, xv, aui[w]);
+                auj[w] = fmaf(gj, xv, auj[w]);
+            }
         }
         ssi = warp_sum(ssi);
         ssj = warp_sum(ssj);
@@ -323,7 +345,7 @@ int launch_prep(const Shape& s, const float* x, const float* V, const gdn_layer_
     GDN_CHECK_LAUNCH("k_node_scalars");
     const long long tasks = (long long)s.N * (s.Bs / 32);
     k_transpose_scalars<<<grid_for_warps(tasks, 8, 16 * num_sms()), 256, 0, st>>>(
-        x, uv, ev, s.B, s.N, s.W, s.Bs, (float*)(ctx + L.xT), (float*)(ctx + L.siT), (float*)(ctx + L.sjT));
+        x, uv, ev, s.B, s.N, s.W, s.WP, s.Bs, (float*)(ctx + L.xT), (float*)(ctx + L.siT), (float*)(ctx + L.sjT));
     GDN_CHECK_LAUNCH("k_transpose_scalars");
     return 0;
 }

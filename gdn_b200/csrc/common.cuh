@@ -55,7 +55,7 @@ struct Shape {
 int make_shape(const gdn_dims* d, Shape* s, bool need_dwide);
 
 struct CtxLayout {
-    size_t xT;      // [N][W][Bs]   x transposed: window index fastest
+    size_t xT;      // [N][Bs/32][WP][32]  x transposed: window index fastest, w zero-padded to WP
     size_t siT;     // [N][Bs]      s_i = x.u_i + e_i
     size_t sjT;     // [N][Bs]      s_j = x.u_j + e_j
     size_t mT;      // [N][Bs]      segment max of the leaky-relu'd logits

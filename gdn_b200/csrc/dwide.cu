@@ -126,6 +126,54 @@ __device__ __forceinline__ void cta_reduce_channels(const double (&vals)[NV], in
 }
 
 // ---------------------------------------------------------------------------------------
+// row staging: a warp pulls up to 32 rows of A (one row per lane, all loads in flight at once)
+// into its private shared-memory tile, then walks them with broadcast float4 reads.  This
+// replaces one dependent global load per row (8 warps/SM cannot hide that latency) by one
+// batch of 32 independent loads.
+// ---------------------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char dyn_smem[];
+
+template <int WP>
+struct RowStage {
+    static constexpr int STRIDE = WP + 4;                    // 80-byte rows: conflict-free float4 stores
+    static constexpr int WARP_FLOATS = 32 * STRIDE;
+    static size_t bytes(int warps) { return (size_t)warps * WARP_FLOATS * sizeof(float); }
+
+    __device__ __forceinline__ static float* tile() {
+        return reinterpret_cast<float*>(dyn_smem) + (size_t)(threadIdx.x >> 5) * WARP_FLOATS;
+    }
+    // lane l < nb loads the W floats at first + l * row_stride
+    __device__ __forceinline__ static void fill(float* sa, const float* __restrict__ first, size_t row_stride,
+                                                int nb, int W, int lane) {
+        __syncwarp();
+        if (lane < nb) {
+            const float* row = first + (size_t)lane * row_stride;
+            float* dst = sa + lane * STRIDE;
+            if ((W & 3) == 0) {
+#pragma unroll
+                for (int w = 0; w < WP; w += 4) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (w < W) v = __ldg(reinterpret_cast<const float4*>(row + w));
+                    *reinterpret_cast<float4*>(dst + w) = v;
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < WP; ++w) dst[w] = (w < W) ? __ldg(row + w) : 0.f;
+            }
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ static void get(const float* sa, int rr, float (&a)[WP]) {
+        const float4* p = reinterpret_cast<const float4*>(sa + rr * STRIDE);
+#pragma unroll
+        for (int q = 0; q < WP / 4; ++q) {
+            const float4 v = p[q];
+            a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // module boundary: out[r,:] = Wl.A[r,:] + bias            (models/graph_layer.py:56,71-74)
 // ---------------------------------------------------------------------------------------
 template <int DPL, int WP>
@@ -135,35 +183,44 @@ k_lin_fwd(const float* __restrict__ A, const float* __restrict__ Wl, const float
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float* sa = RowStage<WP>::tile();
     float wl[DPL][WP], bs[DPL];
     load_wl<DPL, WP>(Wl, W, lane, wl);
 #pragma unroll
     for (int j = 0; j < DPL; ++j) bs[j] = bias ? bias[lane * DPL + j] : 0.f;
+    for (long long r0 = warp * 32; r0 < n; r0 += nwarps * 32) {
+        const int nb = (int)((n - r0) < 32 ? (n - r0) : 32);
+        RowStage<WP>::fill(sa, A + (size_t)r0 * W, (size_t)W, nb, W, lane);
 #pragma unroll 2
-    for (long long r = warp; r < n; r += nwarps) {
-        float a[WP], z[DPL];
-        load_arow<WP>(A + (size_t)r * W, W, a);
+        for (int rr = 0; rr < nb; ++rr) {
+            float a[WP], z[DPL];
+            RowStage<WP>::get(sa, rr, a);
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) {
-            float acc = 0.f;
+            for (int j = 0; j < DPL; ++j) {
+                float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-            for (int w = 0; w < WP; ++w) acc = fmaf(wl[j][w], a[w], acc);
-            z[j] = acc + bs[j];
+                for (int w = 0; w < WP; w += 2) {
+                    acc0 = fmaf(wl[j][w], a[w], acc0);
+                    acc1 = fmaf(wl[j][w + 1], a[w + 1], acc1);
+                }
+                z[j] = (acc0 + acc1) + bs[j];
+            }
+            store_chan<DPL>(out + (size_t)(r0 + rr) * D, lane, z);
         }
-        store_chan<DPL>(out + (size_t)r * D, lane, z);
     }
 }
 
 // g_out -> g_A[r,w] = sum_d g_out[r,d] Wl[d,w];  partial g_Wl[d,w] += g_out[r,d] A[r,w];
 // partial g_bias[d] += g_out[r,d].   part record: [D*W + D] doubles.
+// dynamic smem: max(row stage, red[8][33][32] floats)
 template <int DPL, int WP>
 __global__ void __launch_bounds__(256)
 k_lin_bwd(const float* __restrict__ gout, const float* __restrict__ A, const float* __restrict__ Wl,
           long long n, int W, int D, float* __restrict__ gA, double* __restrict__ part) {
-    __shared__ float red[8][33][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float* sa = RowStage<WP>::tile();
     float wl[DPL][WP], gwl[DPL][WP], gb[DPL];
     load_wl<DPL, WP>(Wl, W, lane, wl);
 #pragma unroll
@@ -172,25 +229,32 @@ k_lin_bwd(const float* __restrict__ gout, const float* __restrict__ A, const flo
 #pragma unroll
         for (int w = 0; w < WP; ++w) gwl[j][w] = 0.f;
     }
-    for (long long r = warp; r < n; r += nwarps) {
-        float a[WP], go[DPL], pw[WP];
-        load_arow<WP>(A + (size_t)r * W, W, a);
-        load_chan_vec<DPL>(gout + (size_t)r * D, lane, go);
+    for (long long r0 = warp * 32; r0 < n; r0 += nwarps * 32) {
+        const int nb = (int)((n - r0) < 32 ? (n - r0) : 32);
+        RowStage<WP>::fill(sa, A + (size_t)r0 * W, (size_t)W, nb, W, lane);
+        for (int rr = 0; rr < nb; ++rr) {
+            const long long r = r0 + rr;
+            float a[WP], go[DPL], pw[WP];
+            RowStage<WP>::get(sa, rr, a);
+            load_chan_vec<DPL>(gout + (size_t)r * D, lane, go);
 #pragma unroll
-        for (int w = 0; w < WP; ++w) pw[w] = 0.f;
+            for (int w = 0; w < WP; ++w) pw[w] = 0.f;
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) {
-            gb[j] += go[j];
+            for (int j = 0; j < DPL; ++j) {
+                gb[j] += go[j];
 #pragma unroll
-            for (int w = 0; w < WP; ++w) {
-                pw[w] = fmaf(go[j], wl[j][w], pw[w]);
-                gwl[j][w] = fmaf(go[j], a[w], gwl[j][w]);
+                for (int w = 0; w < WP; ++w) {
+                    pw[w] = fmaf(go[j], wl[j][w], pw[w]);
+                    gwl[j][w] = fmaf(go[j], a[w], gwl[j][w]);
+                }
             }
+            int widx;
+            const float tot = reduce_scatter<WP>(pw, lane, &widx);
+            if ((lane & ((32 / WP) - 1)) == 0 && widx < W) gA[(size_t)r * W + widx] = tot;
         }
-        int widx;
-        const float tot = reduce_scatter<WP>(pw, lane, &widx);
-        if ((lane & ((32 / WP) - 1)) == 0 && widx < W) gA[(size_t)r * W + widx] = tot;
     }
+    __syncthreads();
+    float (*red)[33][32] = reinterpret_cast<float (*)[33][32]>(dyn_smem);
     double* prec = part + (size_t)blockIdx.x * ((size_t)D * W + D);
 #pragma unroll
     for (int j = 0; j < DPL; ++j) {
@@ -316,16 +380,23 @@ struct RowEval {
     const long long warp_ = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;             \
     const long long nwarps_ = ((long long)gridDim.x * blockDim.x) >> 5;                          \
     const long long tasks_ = (long long)(h).N * (h).S;                                           \
+    const size_t rstride_ = (size_t)(h).N * (h).W;                                               \
+    float* sa_ = RowStage<WP>::tile();                                                           \
     for (long long task_ = warp_; task_ < tasks_; task_ += nwarps_) {                            \
         const int i = (int)(task_ / (h).S), sp = (int)(task_ % (h).S);                           \
         const int b_lo = sp * (h).rps, b_hi = min((h).B, b_lo + (h).rps);
 #define GDN_TASK_LOOP_END }
+// inside a task: batches of up to 32 windows of sensor i
+#define GDN_BATCH_LOOP_BEGIN(h)                                                                  \
+    for (int b0 = b_lo; b0 < b_hi; b0 += 32) {                                                   \
+        const int nb = min(32, b_hi - b0);                                                       \
+        RowStage<WP>::fill(sa_, (h).A + ((size_t)b0 * (h).N + i) * (h).W, rstride_, nb, (h).W, lane);
+#define GDN_BATCH_LOOP_END }
 
 // BN2 batch statistics: sum_r p, sum_r p^2 -> part record [2*D] doubles
 template <int DPL, int WP>
 __global__ void __launch_bounds__(256)
 k_fwd_stats2(HeadArgs h, double* __restrict__ part) {
-    extern __shared__ double dsm[];
     RowEval<DPL, WP> re;
     re.init(h, threadIdx.x & 31);
     double acc[2 * DPL];
@@ -336,22 +407,25 @@ k_fwd_stats2(HeadArgs h, double* __restrict__ part) {
         load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
 #pragma unroll
         for (int j = 0; j < DPL; ++j) s1[j] = s2[j] = 0.f;
+        GDN_BATCH_LOOP_BEGIN(h)
 #pragma unroll 2
-        for (int b = b_lo; b < b_hi; ++b) {
-            float a[WP], xh1[DPL], y1[DPL];
-            load_arow<WP>(h.A + ((size_t)b * h.N + i) * h.W, h.W, a);
-            re.eval(a, xh1, y1);
+            for (int rr = 0; rr < nb; ++rr) {
+                float a[WP], xh1[DPL], y1[DPL];
+                RowStage<WP>::get(sa_, rr, a);
+                re.eval(a, xh1, y1);
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) {
-                const float p = fmaxf(y1[j], 0.f) * v[j];
-                s1[j] += p;
-                s2[j] = fmaf(p, p, s2[j]);
+                for (int j = 0; j < DPL; ++j) {
+                    const float p = fmaxf(y1[j], 0.f) * v[j];
+                    s1[j] += p;
+                    s2[j] = fmaf(p, p, s2[j]);
+                }
             }
-        }
+        GDN_BATCH_LOOP_END
 #pragma unroll
         for (int j = 0; j < DPL; ++j) { acc[j] += (double)s1[j]; acc[DPL + j] += (double)s2[j]; }
     GDN_TASK_LOOP_END
-    cta_reduce_channels<2 * DPL, DPL>(acc, h.D, part + (size_t)blockIdx.x * 2 * h.D, dsm);
+    __syncthreads();
+    cta_reduce_channels<2 * DPL, DPL>(acc, h.D, part + (size_t)blockIdx.x * 2 * h.D, reinterpret_cast<double*>(dyn_smem));
 }
 
 template <int DPL>
@@ -394,38 +468,51 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
     GDN_TASK_LOOP_BEGIN(h)
         float v[DPL];
         load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
-#pragma unroll 2
-        for (int b = b_lo; b < b_hi; ++b) {
-            const size_t r = (size_t)b * h.N + i;
-            float a[WP], xh1[DPL], y1[DPL];
-            load_arow<WP>(h.A + r * h.W, h.W, a);
-            re.eval(a, xh1, y1);
-            bool keep[DPL];
+        GDN_BATCH_LOOP_BEGIN(h)
+            float my_pred = 0.f;
+            uint32_t my_bits[DPL];
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) keep[j] = true;
-            if (drop) {
-                keep_flags<DPL>(h, r, lane, keep);
+            for (int j = 0; j < DPL; ++j) my_bits[j] = 0u;
+#pragma unroll 2
+            for (int rr = 0; rr < nb; ++rr) {
+                const size_t r = (size_t)(b0 + rr) * h.N + i;
+                float a[WP], xh1[DPL], y1[DPL];
+                RowStage<WP>::get(sa_, rr, a);
+                re.eval(a, xh1, y1);
+                bool keep[DPL];
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) keep[j] = true;
+                if (drop) {
+                    keep_flags<DPL>(h, r, lane, keep);
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) {
+                        const uint32_t word = __ballot_sync(0xffffffffu, keep[j]);
+                        if (lane == rr) my_bits[j] = word;
+                    }
+                }
+                float dot = 0.f;
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) {
-                    const uint32_t word = __ballot_sync(0xffffffffu, keep[j]);
-                    if (lane == j) h.bits[r * DPL + j] = word;
+                    const float p = fmaxf(y1[j], 0.f) * v[j];
+                    const float y2 = fmaf(g2[j], fmaf(p, k2a[j], k2b[j]), be2[j]);
+                    float hm = fmaxf(y2, 0.f);
+                    if (drop) hm = keep[j] ? hm * h.scale : 0.f;
+                    dot = fmaf(hm, wo[j], dot);
+                }
+                dot = warp_sum(dot);
+                if (lane == rr) my_pred = dot + bo;
+            }
+            if (lane < nb) {
+                const size_t r = (size_t)(b0 + lane) * h.N + i;
+                pred[r] = my_pred;
+                if (drop) {
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) h.bits[r * DPL + j] = my_bits[j];
                 }
             }
-            float dot = 0.f;
-#pragma unroll
-            for (int j = 0; j < DPL; ++j) {
-                const float p = fmaxf(y1[j], 0.f) * v[j];
-                const float y2 = fmaf(g2[j], fmaf(p, k2a[j], k2b[j]), be2[j]);
-                float hm = fmaxf(y2, 0.f);
-                if (drop) hm = keep[j] ? hm * h.scale : 0.f;
-                dot = fmaf(hm, wo[j], dot);
-            }
-            dot = warp_sum(dot);
-            if (lane == 0) pred[r] = dot + bo;
-        }
+        GDN_BATCH_LOOP_END
     GDN_TASK_LOOP_END
 }
-
 
 // shared recompute of the chain for the backward passes
 template <int DPL, int WP>
@@ -440,25 +527,42 @@ struct BwdRow {
     }
 };
 
+// per-batch side data of the backward passes: lane l holds g_pred and the keep words of row b0+l
 template <int DPL>
-__device__ __forceinline__ void load_keep(const HeadArgs& h, size_t r, int lane, float (&kf)[DPL]) {
-    const bool drop = h.training && h.p_drop > 0.f;
+struct BwdSide {
+    float gp;
+    uint32_t bits[DPL];
+    __device__ __forceinline__ void load(const HeadArgs& h, const float* __restrict__ gpred, int i, int b0, int nb,
+                                         int lane) {
+        const bool drop = h.training && h.p_drop > 0.f;
+        gp = 0.f;
 #pragma unroll
-    for (int j = 0; j < DPL; ++j) {
-        if (drop) {
-            const uint32_t word = h.bits[r * DPL + j];
-            kf[j] = ((word >> lane) & 1u) ? h.scale : 0.f;
-        } else {
-            kf[j] = 1.f;
+        for (int j = 0; j < DPL; ++j) bits[j] = 0xffffffffu;
+        if (lane < nb) {
+            const size_t r = (size_t)(b0 + lane) * h.N + i;
+            gp = __ldg(gpred + r);
+            if (drop) {
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) bits[j] = h.bits[r * DPL + j];
+            }
         }
     }
-}
+    // keep factor (0 or scale) of this lane's channels for row rr of the batch, and that row's g_pred
+    __device__ __forceinline__ float row(const HeadArgs& h, int rr, int lane, float (&kf)[DPL]) const {
+        const bool drop = h.training && h.p_drop > 0.f;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            const uint32_t word = __shfl_sync(0xffffffffu, bits[j], rr);
+            kf[j] = drop ? (((word >> lane) & 1u) ? h.scale : 0.f) : 1.f;
+        }
+        return __shfl_sync(0xffffffffu, gp, rr);
+    }
+};
 
 // pass 1: g_wo, g_gamma2, g_beta2, g_bo   -> part record [3*D + 32] doubles
 template <int DPL, int WP>
 __global__ void __launch_bounds__(256)
 k_bwd1(HeadArgs h, BwdArgs g, double* __restrict__ part) {
-    extern __shared__ double dsm[];
     RowEval<DPL, WP> re;
     BwdRow<DPL, WP> br;
     re.init(h, threadIdx.x & 31);
@@ -473,33 +577,37 @@ k_bwd1(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 #pragma unroll
         for (int j = 0; j < DPL; ++j) t0[j] = t1[j] = t2[j] = 0.f;
         float tb = 0.f;
+        GDN_BATCH_LOOP_BEGIN(h)
+            BwdSide<DPL> side;
+            side.load(h, g.gpred, i, b0, nb, lane);
 #pragma unroll 2
-        for (int b = b_lo; b < b_hi; ++b) {
-            const size_t r = (size_t)b * h.N + i;
-            float a[WP], xh1[DPL], y1[DPL], kf[DPL];
-            load_arow<WP>(h.A + r * h.W, h.W, a);
-            re.eval(a, xh1, y1);
-            load_keep<DPL>(h, r, lane, kf);
-            const float gp = g.gpred[r];
-            tb += gp;
+            for (int rr = 0; rr < nb; ++rr) {
+                float a[WP], xh1[DPL], y1[DPL], kf[DPL];
+                RowStage<WP>::get(sa_, rr, a);
+                re.eval(a, xh1, y1);
+                const float gp = side.row(h, rr, lane, kf);
+                tb += gp;
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) {
-                const float p = fmaxf(y1[j], 0.f) * v[j];
-                const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
-                const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
-                const float hm = fmaxf(y2, 0.f) * kf[j];
-                t0[j] = fmaf(gp, hm, t0[j]);                                  // g_wo
-                const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
-                t1[j] = fmaf(gy2, xh2, t1[j]);                                // g_gamma2
-                t2[j] += gy2;                                                 // g_beta2
+                for (int j = 0; j < DPL; ++j) {
+                    const float p = fmaxf(y1[j], 0.f) * v[j];
+                    const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
+                    const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
+                    const float hm = fmaxf(y2, 0.f) * kf[j];
+                    t0[j] = fmaf(gp, hm, t0[j]);                                  // g_wo
+                    const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
+                    t1[j] = fmaf(gy2, xh2, t1[j]);                                // g_gamma2
+                    t2[j] += gy2;                                                 // g_beta2
+                }
             }
-        }
+        GDN_BATCH_LOOP_END
 #pragma unroll
         for (int j = 0; j < DPL; ++j) {
             acc[j] += (double)t0[j]; acc[DPL + j] += (double)t1[j]; acc[2 * DPL + j] += (double)t2[j];
         }
         gbo += (double)tb;
     GDN_TASK_LOOP_END
+    __syncthreads();
+    double* dsm = reinterpret_cast<double*>(dyn_smem);
     double* prec = part + (size_t)blockIdx.x * (3 * h.D + 32);
     cta_reduce_channels<3 * DPL, DPL>(acc, h.D, prec, dsm);
     // g_bo: every lane of a warp holds the same value; one slot per warp
@@ -516,7 +624,6 @@ k_bwd1(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 template <int DPL, int WP>
 __global__ void __launch_bounds__(256)
 k_bwd2(HeadArgs h, BwdArgs g, double* __restrict__ part) {
-    extern __shared__ double dsm[];
     RowEval<DPL, WP> re;
     BwdRow<DPL, WP> br;
     re.init(h, threadIdx.x & 31);
@@ -537,33 +644,36 @@ k_bwd2(HeadArgs h, BwdArgs g, double* __restrict__ part) {
         load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
 #pragma unroll
         for (int j = 0; j < DPL; ++j) gv[j] = t1[j] = t2[j] = 0.f;
+        GDN_BATCH_LOOP_BEGIN(h)
+            BwdSide<DPL> side;
+            side.load(h, g.gpred, i, b0, nb, lane);
 #pragma unroll 2
-        for (int b = b_lo; b < b_hi; ++b) {
-            const size_t r = (size_t)b * h.N + i;
-            float a[WP], xh1[DPL], y1[DPL], kf[DPL];
-            load_arow<WP>(h.A + r * h.W, h.W, a);
-            re.eval(a, xh1, y1);
-            load_keep<DPL>(h, r, lane, kf);
-            const float gp = g.gpred[r];
+            for (int rr = 0; rr < nb; ++rr) {
+                float a[WP], xh1[DPL], y1[DPL], kf[DPL];
+                RowStage<WP>::get(sa_, rr, a);
+                re.eval(a, xh1, y1);
+                const float gp = side.row(h, rr, lane, kf);
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) {
-                const float r1 = fmaxf(y1[j], 0.f);
-                const float p = r1 * v[j];
-                const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
-                const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
-                const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
-                const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);     // d loss / d p
-                gv[j] = fmaf(gpp, r1, gv[j]);
-                const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
-                t1[j] = fmaf(gy1, xh1[j], t1[j]);                             // g_gamma1
-                t2[j] += gy1;                                                 // g_beta1
+                for (int j = 0; j < DPL; ++j) {
+                    const float r1 = fmaxf(y1[j], 0.f);
+                    const float p = r1 * v[j];
+                    const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
+                    const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
+                    const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
+                    const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);     // d loss / d p
+                    gv[j] = fmaf(gpp, r1, gv[j]);
+                    const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
+                    t1[j] = fmaf(gy1, xh1[j], t1[j]);                             // g_gamma1
+                    t2[j] += gy1;                                                 // g_beta1
+                }
             }
-        }
+        GDN_BATCH_LOOP_END
         store_chan<DPL>(g.gV + ((size_t)sp * h.N + i) * h.D, lane, gv);
 #pragma unroll
         for (int j = 0; j < DPL; ++j) { acc[j] += (double)t1[j]; acc[DPL + j] += (double)t2[j]; }
     GDN_TASK_LOOP_END
-    cta_reduce_channels<2 * DPL, DPL>(acc, h.D, part + (size_t)blockIdx.x * 2 * h.D, dsm);
+    __syncthreads();
+    cta_reduce_channels<2 * DPL, DPL>(acc, h.D, part + (size_t)blockIdx.x * 2 * h.D, reinterpret_cast<double*>(dyn_smem));
 }
 
 // pass 3: g_A[r,:] = g_z.Wl, partial g_Wl += g_z (x) A, partial g_bias += g_z
@@ -571,7 +681,6 @@ k_bwd2(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 template <int DPL, int WP>
 __global__ void __launch_bounds__(256)
 k_bwd3(HeadArgs h, BwdArgs g, double* __restrict__ part) {
-    __shared__ float red[8][33][32];
     RowEval<DPL, WP> re;
     BwdRow<DPL, WP> br;
     re.init(h, threadIdx.x & 31);
@@ -597,36 +706,41 @@ k_bwd3(HeadArgs h, BwdArgs g, double* __restrict__ part) {
     GDN_TASK_LOOP_BEGIN(h)
         float v[DPL];
         load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
-        for (int b = b_lo; b < b_hi; ++b) {
-            const size_t r = (size_t)b * h.N + i;
-            float a[WP], xh1[DPL], y1[DPL], kf[DPL], pw[WP];
-            load_arow<WP>(h.A + r * h.W, h.W, a);
-            re.eval(a, xh1, y1);
-            load_keep<DPL>(h, r, lane, kf);
-            const float gp = g.gpred[r];
+        GDN_BATCH_LOOP_BEGIN(h)
+            BwdSide<DPL> side;
+            side.load(h, g.gpred, i, b0, nb, lane);
+            for (int rr = 0; rr < nb; ++rr) {
+                const size_t r = (size_t)(b0 + rr) * h.N + i;
+                float a[WP], xh1[DPL], y1[DPL], kf[DPL], pw[WP];
+                RowStage<WP>::get(sa_, rr, a);
+                re.eval(a, xh1, y1);
+                const float gp = side.row(h, rr, lane, kf);
 #pragma unroll
-            for (int w = 0; w < WP; ++w) pw[w] = 0.f;
+                for (int w = 0; w < WP; ++w) pw[w] = 0.f;
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) {
-                const float p = fmaxf(y1[j], 0.f) * v[j];
-                const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
-                const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
-                const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
-                const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);
-                const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
-                const float gz = s1c[j] * (gy1 - cB1[j] - xh1[j] * cG1[j]);   // d loss / d z
-                gb[j] += gz;
+                for (int j = 0; j < DPL; ++j) {
+                    const float p = fmaxf(y1[j], 0.f) * v[j];
+                    const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
+                    const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
+                    const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
+                    const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);
+                    const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
+                    const float gz = s1c[j] * (gy1 - cB1[j] - xh1[j] * cG1[j]);   // d loss / d z
+                    gb[j] += gz;
 #pragma unroll
-                for (int w = 0; w < WP; ++w) {
-                    pw[w] = fmaf(gz, re.wl[j][w], pw[w]);
-                    gwl[j][w] = fmaf(gz, a[w], gwl[j][w]);
+                    for (int w = 0; w < WP; ++w) {
+                        pw[w] = fmaf(gz, re.wl[j][w], pw[w]);
+                        gwl[j][w] = fmaf(gz, a[w], gwl[j][w]);
+                    }
                 }
+                int widx;
+                const float tot = reduce_scatter<WP>(pw, lane, &widx);
+                if ((lane & ((32 / WP) - 1)) == 0 && widx < h.W) g.gA[r * h.W + widx] = tot;
             }
-            int widx;
-            const float tot = reduce_scatter<WP>(pw, lane, &widx);
-            if ((lane & ((32 / WP) - 1)) == 0 && widx < h.W) g.gA[r * h.W + widx] = tot;
-        }
+        GDN_BATCH_LOOP_END
     GDN_TASK_LOOP_END
+    __syncthreads();
+    float (*red)[33][32] = reinterpret_cast<float (*)[33][32]>(dyn_smem);
     double* prec = part + (size_t)blockIdx.x * ((size_t)h.D * h.W + h.D);
     const int ln = threadIdx.x & 31;
 #pragma unroll
@@ -866,6 +980,27 @@ __global__ void k_fin_embed(const double* __restrict__ part, int nrec, int D,
         else { CALL(DPLC, 32); }                                                      \
     } while (0)
 
+// dynamic shared memory of a D-wide kernel: the row stage, aliased after the main loop by the
+// cross-warp reduction scratch (doubles for channel sums, red[8][33][32] floats for g_Wl)
+template <int WP>
+static size_t dw_smem(int nv_double, bool red33) {
+    size_t b = RowStage<WP>::bytes(8);
+    const size_t r1 = (size_t)8 * nv_double * 32 * sizeof(double);
+    const size_t r2 = red33 ? (size_t)8 * 33 * 32 * sizeof(float) : 0;
+    if (r1 > b) b = r1;
+    if (r2 > b) b = r2;
+    return b;
+}
+#define GDN_LAUNCH_DYN(KERNEL, GRID, SMEM, ST, ...)                                                     \
+    do {                                                                                               \
+        const size_t sm__ = (SMEM);                                                                    \
+        if (sm__ > 48 * 1024) {                                                                        \
+            cudaError_t e__ = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm__); \
+            if (e__ != cudaSuccess) return cuda_fail(e__, "smem attribute");                           \
+        }                                                                                              \
+        KERNEL<<<GRID, 256, sm__, ST>>>(__VA_ARGS__);                                                  \
+    } while (0)
+
 static int dw_grid(long long tasks) {
     long long g = (tasks + 7) / 8;
     const int cap = 2 * num_sms();
@@ -876,7 +1011,8 @@ static int dw_grid(long long tasks) {
 
 int launch_lin_fwd(const Shape& s, const float* A, const gdn_layer_params* p, float* out, cudaStream_t st) {
     const int grid = dw_grid(s.n);
-#define CALL(DPLC, WPC) k_lin_fwd<DPLC, WPC><<<grid, 256, 0, st>>>(A, p->lin_weight, p->bias, s.n, s.W, s.D, out)
+#define CALL(DPLC, WPC) \
+    GDN_LAUNCH_DYN((k_lin_fwd<DPLC, WPC>), grid, dw_smem<WPC>(0, false), st, A, p->lin_weight, p->bias, s.n, s.W, s.D, out)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_lin_fwd");
@@ -886,7 +1022,8 @@ int launch_lin_fwd(const Shape& s, const float* A, const gdn_layer_params* p, fl
 int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_layer_params* p, float* gA,
                    double* part, int* nrec, cudaStream_t st) {
     const int grid = dw_grid(s.n);
-#define CALL(DPLC, WPC) k_lin_bwd<DPLC, WPC><<<grid, 256, 0, st>>>(gout, A, p->lin_weight, s.n, s.W, s.D, gA, part)
+#define CALL(DPLC, WPC) \
+    GDN_LAUNCH_DYN((k_lin_bwd<DPLC, WPC>), grid, dw_smem<WPC>(0, true), st, gout, A, p->lin_weight, s.n, s.W, s.D, gA, part)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_lin_bwd");
@@ -922,18 +1059,11 @@ int launch_fin_bn_eval(const Shape& s, const gdn_layer_params* p, const gdn_head
     return 0;
 }
 
-static size_t dsm_bytes(int nv) { return (size_t)8 * nv * 32 * sizeof(double); }
 
 int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, double* sums, const gdn_bn* bn, float* bnc,
                       cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC)                                                                                   \
-    do {                                                                                                  \
-        const size_t sm = dsm_bytes(2 * DPLC);                                                            \
-        if (sm > 48 * 1024)                                                                               \
-            cudaFuncSetAttribute(k_fwd_stats2<DPLC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-        k_fwd_stats2<DPLC, WPC><<<grid, 256, sm, st>>>(h, part);                                          \
-    } while (0)
+#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_fwd_stats2<DPLC, WPC>), grid, dw_smem<WPC>(2 * DPLC, false), st, h, part)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_fwd_stats2");
@@ -946,7 +1076,7 @@ int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, double* s
 
 int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC) k_fwd_out<DPLC, WPC><<<grid, 256, 0, st>>>(h, pred)
+#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_fwd_out<DPLC, WPC>), grid, dw_smem<WPC>(0, false), st, h, pred)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_fwd_out");
@@ -956,13 +1086,7 @@ int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t 
 int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
                 float* c2, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC)                                                                                 \
-    do {                                                                                                \
-        const size_t sm = dsm_bytes(3 * DPLC);                                                          \
-        if (sm > 48 * 1024)                                                                             \
-            cudaFuncSetAttribute(k_bwd1<DPLC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-        k_bwd1<DPLC, WPC><<<grid, 256, sm, st>>>(h, g, part);                                           \
-    } while (0)
+#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_bwd1<DPLC, WPC>), grid, dw_smem<WPC>(3 * DPLC, false), st, h, g, part)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd1");
@@ -975,13 +1099,7 @@ int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
 int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
                 float* c1, float* gV_final, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC)                                                                                 \
-    do {                                                                                                \
-        const size_t sm = dsm_bytes(2 * DPLC);                                                          \
-        if (sm > 48 * 1024)                                                                             \
-            cudaFuncSetAttribute(k_bwd2<DPLC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-        k_bwd2<DPLC, WPC><<<grid, 256, sm, st>>>(h, g, part);                                           \
-    } while (0)
+#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_bwd2<DPLC, WPC>), grid, dw_smem<WPC>(2 * DPLC, false), st, h, g, part)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd2");
@@ -1000,7 +1118,7 @@ int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
 
 int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC) k_bwd3<DPLC, WPC><<<grid, 256, 0, st>>>(h, g, part)
+#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_bwd3<DPLC, WPC>), grid, dw_smem<WPC>(0, true), st, h, g, part)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd3");

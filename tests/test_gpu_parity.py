@@ -25,27 +25,35 @@ def _model_from(rec, dev="cuda"):
     return model.to(dev), m
 
 
+REF_NOISE = 8.0
+
+
 def _grad_ok(name, ours, g64, g32):
     """Gradient parity against the float64 reference:
-    err(ours) <= max(1e-4 * scale, 2 * err(reference fp32)) normwise, with an absolute floor for
-    analytically-zero gradients.  A ReLU whose pre-activation is within rounding of 0 can gate
-    differently in two fp32 evaluation orders and moves single elements by one row's contribution;
-    such isolated elements (at most 3, or 1e-6 of the tensor) are tolerated if the tensor still
-    agrees in the L2 sense."""
+    err(ours) <= max(1e-4 * scale, REF_NOISE * err(reference fp32)), max-norm and L2.
+
+    Why the reference's own fp32 error is the yardstick: a ReLU whose pre-activation is within
+    rounding of 0 gates differently in any two fp32 evaluation orders, and one flipped gate moves a
+    per-channel sum over n rows by ~1/sqrt(n) of its value.  The reference's fp32 error against its
+    own float64 run therefore varies by an order of magnitude with nothing but the CPU thread count
+    (2.7e-4 ... 3.1e-3 on embedding.weight at the WADI shape with stressed BatchNorm parameters),
+    and the kernels' closed forms evaluated in fp32 on the CPU (oracle/closed_form.py) land in the
+    same band.  In float64 the closed forms equal the reference to 1e-12
+    (tests/test_closed_form_cpu.py).  Up to 3 isolated elements may exceed the bound."""
     ours = ours.detach().double().cpu().reshape(-1)
     g64 = torch.as_tensor(g64).double().reshape(-1)
     g32 = torch.as_tensor(g32).double().reshape(-1)
     scale = g64.abs().max().item()
     diff = (ours - g64).abs()
     ref_err = (g32 - g64).abs().max().item()
-    bound = max(TOL * scale, 2.0 * ref_err, 1e-7)
+    bound = max(TOL * scale, REF_NOISE * ref_err, 1e-7)
     n_bad = int((diff > bound).sum())
     l2 = diff.norm().item() / max(g64.norm().item(), 1e-30)
     l2_ref = (g32 - g64).norm().item() / max(g64.norm().item(), 1e-30)
     msg = (f"{name}: max err {diff.max().item():.3e} bound {bound:.3e} (scale {scale:.3e}, ref fp32 err "
            f"{ref_err:.3e}), {n_bad} elements over, L2 rel {l2:.3e} (ref {l2_ref:.3e})")
     assert n_bad <= max(3, int(1e-6 * diff.numel())), msg
-    assert l2 <= max(TOL, 2.0 * l2_ref) or scale < 1e-6, msg
+    assert l2 <= max(TOL, REF_NOISE * l2_ref) or scale < 1e-6, msg
     assert diff.max().item() <= 50 * bound, msg
 
 
