@@ -1,0 +1,537 @@
+// gram_tc.cu -- tensor-core engine of the learned-graph builder for large sensor counts
+// (models/GDN.py:143-159).
+//
+// The N x N cosine Gram is a dense contraction, so at large N it belongs on the 5th-generation
+// tensor cores.  fp32 ranking accuracy is kept by a split-precision product followed by an exact
+// re-score:
+//   1. k_normalise_split: vn = v / |v| (fp32), split into two bf16 matrices hi + lo = vn
+//      (|vn - hi - lo| <= 2^-18 |vn|).
+//   2. k_gram_tc (this file's tcgen05 kernel): one CTA owns 128 rows and sweeps the columns in
+//      tiles of 64.  Operand tiles arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B, K-major);
+//      one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=64, K=16) for the
+//      three products hi.hi + hi.lo + lo.hi into a double-buffered TMEM accumulator; four epilogue
+//      warps pull the tile out of TMEM with tcgen05.ld (thread <-> row), filter it against the
+//      row's running threshold and keep the best L = K + 8 candidates per row in shared memory.
+//      The [N, N] matrix is never written.  |approx - exact| <= eps = 3e-5 (3 * 2^-18 from the
+//      dropped lo.lo term and the split residuals, plus fp32 accumulation).
+//   3. k_rescore: the L candidates of every row are re-scored with the SAME fp32 fmaf chain the
+//      exact engine uses (graph_build.cu) and ranked (value desc, index asc) -> bit-identical
+//      output.  A row whose 8 spare candidates all sit within 2*eps of the K-th approximate value
+//      could have lost a true neighbour: its 64-row block is flagged and recomputed by the exact
+//      engine (never observed on non-degenerate embeddings; exercised by the tests with duplicates).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "launchers.h"
+
+namespace gdn {
+
+constexpr int TC_BM = 128;        // rows per CTA = UMMA M
+constexpr int TC_BN = 64;         // columns per tile = UMMA N
+constexpr int TC_BK = 64;         // bf16 per k-block: 128 bytes = one SWIZZLE_128B atom row
+constexpr int TC_STAGES = 4;
+constexpr int TC_SLACK = 8;
+constexpr int TC_MAXL = 80;
+constexpr int TC_MAXC = 256;      // buffer capacity (8 entries per lane in a compaction)
+constexpr float TC_EPS = 3e-5f;
+constexpr uint32_t TC_SPIN = 1u << 22;   // bounded mbarrier spins: a protocol bug must not hang the GPU
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    for (uint32_t it = 0; it < TC_SPIN; ++it)
+        if (mbar_try_wait(bar, parity)) return true;
+    atomicExch(err, code);
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4,
+// LBO = 0 (a single swizzle atom along K), SBO = 1024 bytes (8 rows x 128 bytes), version 1.
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, N = 64, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                              ((uint32_t)(TC_BM >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------
+// 1. normalise + split
+// ---------------------------------------------------------------------------------------
+__global__ void k_normalise_split(const float* __restrict__ V, int N, int D, float* __restrict__ nrm,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < N; i += nwarps) {
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float v = V[(size_t)i * D + d];
+            s = fmaf(v, v, s);
+        }
+        s = warp_sum(s);
+        const float n = sqrtf(s);                   // same value k_row_norms produces
+        if (lane == 0) nrm[i] = n;
+        for (int d = lane; d < D; d += 32) {
+            const float vn = V[(size_t)i * D + d] / n;
+            const __nv_bfloat16 h = __float2bfloat16_rn(vn);
+            const __nv_bfloat16 l = __float2bfloat16_rn(vn - __bfloat162float(h));
+            hi[(size_t)i * D + d] = h;
+            lo[(size_t)i * D + d] = l;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// 2. tcgen05 Gram + per-row candidate selection
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+          int N, int KB, int L, int C, float* __restrict__ bufv, int* __restrict__ bufj, int* __restrict__ rowcnt,
+          int* __restrict__ err, int dbg) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B atoms: 1024-byte aligned
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t A_BYTES = (uint32_t)KB * TC_BM * 128;                 // one of hi / lo
+    const uint32_t B_BYTES = (uint32_t)KB * TC_BN * 128;                 // one of hi / lo, one stage
+    const uint32_t sA = base;                                            // [2][KB][128 x 128 B]
+    const uint32_t sB = sA + 2 * A_BYTES;                                // [STAGES][2][KB][64 x 128 B]
+    const uint32_t off_stage = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES;
+    float* p_vals = reinterpret_cast<float*>(gbase + off_stage);         // [17][128] filter staging (slot 16 = trash)
+    int* p_idxs = reinterpret_cast<int*>(p_vals + 17 * TC_BM);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_idxs + 17 * TC_BM);
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t b_afull = bar0, b_full = bar0 + 8, b_empty = b_full + 8 * TC_STAGES,
+                   b_tfull = b_empty + 8 * TC_STAGES, b_tempty = b_tfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * TC_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM;
+    const int ntiles = (N + TC_BN - 1) / TC_BN;
+
+    if (threadIdx.x == 0) {
+        mbar_init(b_afull, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(b_tfull + 8 * a, 1); mbar_init(b_tempty + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(2u * TC_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        mbar_expect_tx(b_afull, 2 * A_BYTES);
+        for (int h = 0; h < 2; ++h)
+            for (int kb = 0; kb < KB; ++kb)
+                for (int half = 0; half < 2; ++half)
+                    tma_load_2d(sA + h * A_BYTES + kb * (TC_BM * 128) + half * (64 * 128), h ? &tm_lo : &tm_hi, b_afull,
+                                kb * TC_BK, m0 + half * 64);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % TC_STAGES;
+            const uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u;
+            if (!mbar_wait(b_empty + 8 * s, ph ^ 1u, err, 1)) break;
+            mbar_expect_tx(b_full + 8 * s, 2 * B_BYTES);
+            for (int h = 0; h < 2; ++h)
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(sB + (s * 2 + h) * B_BYTES + kb * (TC_BN * 128), h ? &tm_lo : &tm_hi, b_full + 8 * s,
+                                kb * TC_BK, t * TC_BN);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer (one thread) =====
+        bool ok = mbar_wait(b_afull, 0, err, 2);
+        for (int t = 0; ok && t < ntiles; ++t) {
+            const int s = t % TC_STAGES, acc = t & 1;
+            const uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u, aph = (uint32_t)(t >> 1) & 1u;
+            if (!mbar_wait(b_tempty + 8 * acc, aph ^ 1u, err, 3)) break;
+            if (!mbar_wait(b_full + 8 * s, ph, err, 4)) break;
+            tc_fence_after();
+            uint32_t accumulate = 0;
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {                      // hi.hi, hi.lo, lo.hi
+                const int ah = prod == 2 ? 1 : 0, bh = prod == 1 ? 1 : 0;
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint32_t a0 = sA + ah * A_BYTES + kb * (TC_BM * 128);
+                    const uint32_t b0 = sB + (s * 2 + bh) * B_BYTES + kb * (TC_BN * 128);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        tc_mma_f16(tmem_base + acc * TC_BN, sw128_desc(a0 + k * 32), sw128_desc(b0 + k * 32), TC_IDESC,
+                                   accumulate);
+                        accumulate = 1;
+                    }
+                }
+            }
+            tc_commit(b_empty + 8 * s);          // smem stage reusable once these MMAs have read it
+            tc_commit(b_tfull + 8 * acc);        // accumulator ready for the epilogue
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread <-> row =====
+        // Selection of the best L entries of every row, thread <-> row for the streaming part:
+        //   * a thread appends every value above its row's threshold to the row's buffer (capacity
+        //     C = 2L, global memory, L2-resident; the append is two fire-and-forget stores);
+        //   * when a buffer could overflow within the next 16 columns the warp compacts it
+        //     cooperatively: rank every entry (value desc, position asc), keep ranks < L at slot =
+        //     rank, and raise the threshold to the L-th value.  The threshold is only refreshed at
+        //     compactions, so a row is compacted ~1 + ln(N / 2L) times per sweep instead of paying a
+        //     minimum search per admitted element.
+        const int wrow0 = (warp - 4) * 32;           // first row of this warp inside the CTA
+        const int row = wrow0 + lane;
+        float* bv = bufv + (size_t)(m0 + row) * C;
+        int* bj = bufj + (size_t)(m0 + row) * C;
+        float* pv = p_vals + row;                    // staging slot q of row r at [q * 128 + r]; slot 16 = trash
+        int* pj = p_idxs + row;
+        int cnt = 0;
+        float thr = -INFINITY;
+        constexpr int NE = TC_MAXC / 32;
+        // order-preserving float <-> unsigned key
+        auto to_key = [](float f) -> unsigned {
+            const unsigned b = __float_as_uint(f);
+            return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+        };
+        auto from_key = [](unsigned k) -> float {
+            return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+        };
+        // Cooperative compaction of the rows in `todo`: find the L-th largest key by bisection on its
+        // bits (32 warp-wide counts), keep the L best entries (ties by position) in slots 0..L-1.
+        auto compact = [&](unsigned todo) {
+            while (todo) {
+                const int rr = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int cnt_r = __shfl_sync(0xffffffffu, cnt, rr);
+                float* gv = bufv + (size_t)(m0 + wrow0 + rr) * C;
+                int* gj = bufj + (size_t)(m0 + wrow0 + rr) * C;
+                unsigned key[NE];
+                int ej[NE];
+#pragma unroll
+                for (int t = 0; t < NE; ++t) {
+                    const int e = lane + 32 * t;
+                    const bool valid = e < cnt_r;
+                    key[t] = valid ? to_key(gv[e]) : 0u;            // key 0 (= -NaN pattern) sorts last
+                    ej[t] = valid ? gj[e] : -1;
+                }
+                if (cnt_r > L) {
+                    unsigned T = 0u;
+#pragma unroll 1
+                    for (int bit = 30; bit >= 0; bit -= 2) {          // two key bits per step
+                        const unsigned c1 = T | (1u << bit), c2 = T | (2u << bit), c3 = T | (3u << bit);
+                        unsigned c = 0;                                   // three counts (<= 256 each), 10 bits apiece
+#pragma unroll
+                        for (int t = 0; t < NE; ++t)
+                            c += (key[t] >= c1 ? 1u : 0u) + (key[t] >= c2 ? 1u << 10 : 0u) + (key[t] >= c3 ? 1u << 20 : 0u);
+                        c = __reduce_add_sync(0xffffffffu, c);
+                        const int n1 = c & 1023, n2 = (c >> 10) & 1023, n3 = c >> 20;
+                        T = n3 >= L ? c3 : (n2 >= L ? c2 : (n1 >= L ? c1 : T));
+                    }
+                    int n_gt = 0;
+#pragma unroll
+                    for (int t = 0; t < NE; ++t) n_gt += (key[t] > T) ? 1 : 0;
+                    n_gt = __reduce_add_sync(0xffffffffu, n_gt);
+                    const int need_eq = L - n_gt;                    // >= 1 entries equal to T are kept
+                    const unsigned lt = (1u << lane) - 1u;
+                    int eq_before = 0, kept_before = 0;
+#pragma unroll
+                    for (int t = 0; t < NE; ++t) {
+                        const bool is_eq = key[t] == T;
+                        const unsigned eqm = __ballot_sync(0xffffffffu, is_eq);
+                        const int eq_rank = eq_before + __popc(eqm & lt);
+                        const bool keep = key[t] > T || (is_eq && eq_rank < need_eq);
+                        const unsigned km = __ballot_sync(0xffffffffu, keep);
+                        if (keep) {
+                            const int slot = kept_before + __popc(km & lt);
+                            gv[slot] = from_key(key[t]);
+                            gj[slot] = ej[t];
+                        }
+                        eq_before += __popc(eqm);
+                        kept_before += __popc(km);
+                    }
+                    if (lane == rr) { thr = from_key(T); cnt = L; }
+                }
+                __syncwarp();
+            }
+        };
+        // The code of this loop is kept SMALL on purpose (one compaction site, one 16-column filter
+        // body looped four times): with a single warp per scheduler an instruction-cache miss is fully
+        // exposed, and the fully unrolled version (111 KB of SASS) spent most of its time in
+        // stall_no_inst.
+        bool ok = true;
+#pragma unroll 1
+        for (int t = 0; t <= ntiles; ++t) {
+            // compaction point: once per tile (the tile can append at most 64), and once at the very end
+            const unsigned need = __ballot_sync(0xffffffffu, t == ntiles ? cnt > L : cnt + TC_BN > C);
+            if (need) compact(need);
+            if (t == ntiles) break;
+            const int acc = t & 1;
+            const uint32_t aph = (uint32_t)(t >> 1) & 1u;
+            if (!mbar_wait(b_tfull + 8 * acc, aph, err, 5)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * TC_BN;
+            const int j0 = t * TC_BN;
+#pragma unroll 1
+            for (int grp = 0; grp < 4; ++grp) {
+                uint32_t r[16];
+                tmem_ld16(taddr + grp * 16, r);
+                tmem_wait_ld();
+                if (grp == 3) {                                      // whole tile read: TMEM stage is free again
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b_tempty + 8 * acc);
+                }
+                if (dbg & 1) continue;
+                const int lim = N - j0 - grp * 16;                   // columns >= lim are padding
+                unsigned mask = 0u;
+#pragma unroll
+                for (int cc = 0; cc < 16; ++cc)
+                    mask |= ((cc < lim) & (__uint_as_float(r[cc]) > thr)) ? (1u << cc) : 0u;
+                const int np = __popc(mask);
+                if (__any_sync(0xffffffffu, mask != 0u)) {
+                    // branch-free staging: passing columns to consecutive slots, the rest to the trash slot
+#pragma unroll
+                    for (int cc = 0; cc < 16; ++cc) {
+                        const int slot = (mask >> cc) & 1u ? __popc(mask & ((1u << cc) - 1u)) : 16;
+                        pv[slot * TC_BM] = __uint_as_float(r[cc]);
+                        pj[slot * TC_BM] = j0 + grp * 16 + cc;
+                    }
+                    for (int q = 0; q < np; ++q) {
+                        bv[cnt + q] = pv[q * TC_BM];
+                        bj[cnt + q] = pj[q * TC_BM];
+                    }
+                    cnt += np;
+                }
+            }
+        }
+        if (ok && m0 + row < N) rowcnt[m0 + row] = cnt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * TC_BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// 3. exact re-score + ranking of the candidates (one warp per row)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int D, int K, int L, int C,
+          const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ rowcnt,
+          int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, int* __restrict__ block_flags) {
+    __shared__ float s_cos[8][TC_MAXL];
+    __shared__ int s_j[8][TC_MAXL];
+    __shared__ int s_out[8][TC_MAXL];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * 8 + wid;
+    if (i >= N) return;
+    const float* vi = V + (size_t)i * D;
+    const float ni = nrm[i];
+    const int have = rowcnt[i];
+    float amin = INFINITY;
+    for (int l = lane; l < L; l += 32) {
+        const int j = l < have ? cand_idx[(size_t)i * C + l] : -1;
+        float c = -INFINITY;
+        if (j >= 0) {
+            // one fmaf chain over d = 0..D-1, exactly as graph_build.cu accumulates it; 16-byte loads
+            const float4* vi4 = reinterpret_cast<const float4*>(vi);
+            const float4* vj4 = reinterpret_cast<const float4*>(V + (size_t)j * D);
+            float dot = 0.f;
+#pragma unroll 8
+            for (int q = 0; q < D / 4; ++q) {
+                const float4 a = __ldg(vi4 + q), b = __ldg(vj4 + q);
+                dot = fmaf(a.x, b.x, dot);
+                dot = fmaf(a.y, b.y, dot);
+                dot = fmaf(a.z, b.z, dot);
+                dot = fmaf(a.w, b.w, dot);
+            }
+            c = dot / (ni * nrm[j]);
+        }
+        s_cos[wid][l] = c;
+        s_j[wid][l] = j;
+        amin = fminf(amin, l < have ? cand_val[(size_t)i * C + l] : -INFINITY);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+    int above = 0;
+    for (int l = lane; l < L && l < have; l += 32) above += cand_val[(size_t)i * C + l] > amin + 2.f * TC_EPS ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+    if (lane == 0 && above < K) block_flags[i / 64] = 1;      // the slack window is ambiguous: exact fix-up
+    __syncwarp();
+    for (int l = lane; l < L; l += 32) {
+        const float c = s_cos[wid][l];
+        const int j = s_j[wid][l];
+        int rank = 0;
+        for (int q = 0; q < L; ++q) {
+            const float cq = s_cos[wid][q];
+            const int jq = s_j[wid][q];
+            rank += (cq > c || (cq == c && jq < j)) ? 1 : 0;
+        }
+        if (j >= 0 && rank < K) s_out[wid][rank] = j;
+    }
+    __syncwarp();
+    if (idx_out != nullptr)
+        for (int k = lane; k < K; k += 32) idx_out[(size_t)i * K + k] = (int64_t)s_out[wid][k];
+    if (nbr_out != nullptr && lane == 0) {
+        int32_t* nb = nbr_out + (size_t)i * (K + 1);
+        int o = 0;
+        for (int k = 0; k < K; ++k) {
+            const int j = s_out[wid][k];
+            if (j != i) nb[o++] = j;
+        }
+        nb[o++] = i;
+        for (; o < K + 1; ++o) nb[o] = -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }
+    return fn;
+}
+
+bool gram_tc_supported(int N, int D, int K) {
+    return N >= 1024 && (D == 64 || D == 128) && K + TC_SLACK <= TC_MAXL && K + TC_SLACK <= N;
+}
+
+size_t gram_tc_ws_bytes(int N, int D, int K) {
+    const int C = TC_MAXC;
+    (void)K;
+    const size_t Npad = (size_t)ceil_div(N, TC_BM) * TC_BM;
+    size_t b = align_up((size_t)N * sizeof(float), 256);
+    b += 2 * align_up((size_t)N * D * sizeof(__nv_bfloat16), 256);
+    b += 2 * align_up(Npad * C * sizeof(float), 256);
+    b += align_up((size_t)N * sizeof(int), 256);
+    b += align_up(((size_t)(N + 63) / 64 + 68) * sizeof(int), 256);
+    return b;
+}
+
+int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, cudaStream_t st,
+                   float** nrm_out, int** flags_out) {
+    const int L = K + TC_SLACK, C = TC_MAXC, KB = D / TC_BK;
+    const size_t Npad = (size_t)ceil_div(N, TC_BM) * TC_BM;
+    char* p = (char*)ws;
+    float* nrm = (float*)p;                 p += align_up((size_t)N * sizeof(float), 256);
+    __nv_bfloat16* hi = (__nv_bfloat16*)p;  p += align_up((size_t)N * D * sizeof(__nv_bfloat16), 256);
+    __nv_bfloat16* lo = (__nv_bfloat16*)p;  p += align_up((size_t)N * D * sizeof(__nv_bfloat16), 256);
+    float* bufv = (float*)p;                p += align_up(Npad * C * sizeof(float), 256);
+    int* bufj = (int*)p;                    p += align_up(Npad * C * sizeof(float), 256);
+    int* rowcnt = (int*)p;                  p += align_up((size_t)N * sizeof(int), 256);
+    int* flags = (int*)p;                   // [ceil(N/64)] block flags, then the error word
+    const int nblk64 = (N + 63) / 64;
+    int* err = flags + nblk64;
+    cudaError_t e = cudaMemsetAsync(flags, 0, ((size_t)nblk64 + 68) * sizeof(int), st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset flags");
+
+    int g = ceil_div(N, 8);
+    if (g > 8 * num_sms()) g = 8 * num_sms();
+    k_normalise_split<<<g, 256, 0, st>>>(V, N, D, nrm, hi, lo);
+    GDN_CHECK_LAUNCH("k_normalise_split");
+
+    PFN_cuTensorMapEncodeTiled_v12000 encode = get_encode();
+    GDN_CHECK_ARG(encode != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap tm_hi, tm_lo;
+    const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
+    const cuuint64_t gstr[1] = {(cuuint64_t)D * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, 64u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r1 = encode(&tm_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&tm_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, lo, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GDN_CHECK_ARG(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+
+    const size_t smem = 1024 + (size_t)2 * KB * TC_BM * 128 + (size_t)TC_STAGES * 2 * KB * TC_BN * 128 +
+                        (size_t)2 * 17 * TC_BM * sizeof(float) + (4 + 2 * TC_STAGES + 4) * 8 + 16;
+    GDN_CHECK_ARG(smem <= 227 * 1024, "gram_tc: %zu bytes of shared memory needed", smem);
+    e = cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "smem attr k_gram_tc");
+    static int dbg = -1;
+    if (dbg < 0) { const char* e_ = getenv("GDN_TC_DBG"); dbg = e_ ? atoi(e_) : 0; }
+    k_gram_tc<<<ceil_div(N, TC_BM), 256, smem, st>>>(tm_hi, tm_lo, N, KB, L, C, bufv, bufj, rowcnt, err, dbg);
+    GDN_CHECK_LAUNCH("k_gram_tc");
+    k_rescore<<<ceil_div(N, 8), 256, 0, st>>>(V, nrm, N, D, K, L, C, bufv, bufj, rowcnt, idx, nbr, flags);
+    GDN_CHECK_LAUNCH("k_rescore");
+    *nrm_out = nrm;
+    *flags_out = flags;
+    return 0;
+}
+
+}  // namespace gdn

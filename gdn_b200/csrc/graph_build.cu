@@ -76,7 +76,8 @@ __device__ __forceinline__ void list_insert(float* vals, int* idxs, int* cnt_p, 
 // dynamic smem: lists  vals[GB_TI][K] (float), idxs[GB_TI][K] (int)
 __global__ void __launch_bounds__(256)
 k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, int D, int K,
-            int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out) {
+            int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, const int* __restrict__ block_flags) {
+    if (block_flags != nullptr && block_flags[blockIdx.x] == 0) return;   // fix-up mode: flagged blocks only
     __shared__ float As[GB_TI][GB_DC + 1];
     __shared__ float Bs[GB_TJ][GB_DC + 1];
     __shared__ float Cs[GB_TI][GB_TJ + 1];
@@ -181,27 +182,48 @@ k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, i
     }
 }
 
+// gram_tc.cu
+bool gram_tc_supported(int N, int D, int K);
+size_t gram_tc_ws_bytes(int N, int D, int K);
+int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, cudaStream_t st,
+                   float** nrm_out, int** flags_out);
+
 size_t graph_build_ws_bytes(int N, int D, int K) {
-    (void)D; (void)K;
-    return align_up((size_t)N * sizeof(float), 256);
+    size_t b = align_up((size_t)N * sizeof(float), 256);
+    if (gram_tc_supported(N, D, K)) {
+        const size_t t = gram_tc_ws_bytes(N, D, K);
+        if (t > b) b = t;
+    }
+    return b;
 }
 
 int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, size_t ws_bytes,
                        int use_tc, cudaStream_t st) {
     GDN_CHECK_ARG(K <= GB_MAXK, "topk K=%d unsupported (max %d)", K, GB_MAXK);
     GDN_CHECK_ARG(ws != nullptr && ws_bytes >= graph_build_ws_bytes(N, D, K), "graph_build: workspace too small");
-    GDN_CHECK_ARG(use_tc <= 0, "graph_build: the tcgen05 Gram path is not built into this library yet");
-    float* nrm = (float*)ws;
-    int g = ceil_div(N, 8);
-    if (g > 8 * num_sms()) g = 8 * num_sms();
-    k_row_norms<<<g, 256, 0, st>>>(V, N, D, nrm);
-    GDN_CHECK_LAUNCH("k_row_norms");
+    const bool tc_ok = gram_tc_supported(N, D, K);
+    GDN_CHECK_ARG(use_tc <= 0 || tc_ok,
+                  "graph_build: the tcgen05 engine needs N >= 1024, dim 64 or 128, topk <= 72 (N=%d D=%d K=%d)", N, D, K);
     const size_t smem = (size_t)GB_TI * K * (sizeof(float) + sizeof(int));
     {
         cudaError_t e = cudaFuncSetAttribute(k_gram_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "smem attr k_gram_topk");
     }
-    k_gram_topk<<<ceil_div(N, GB_TI), 256, smem, st>>>(V, nrm, N, D, K, idx, nbr);
+    if (use_tc > 0 || (use_tc < 0 && tc_ok)) {
+        float* nrm = nullptr;
+        int* flags = nullptr;
+        if (int rc = launch_gram_tc(V, N, D, K, idx, nbr, ws, st, &nrm, &flags)) return rc;
+        // exact fix-up of the (normally zero) 64-row blocks whose candidate window was ambiguous
+        k_gram_topk<<<ceil_div(N, GB_TI), 256, smem, st>>>(V, nrm, N, D, K, idx, nbr, flags);
+        GDN_CHECK_LAUNCH("k_gram_topk_fixup");
+        return 0;
+    }
+    float* nrm = (float*)ws;
+    int g = ceil_div(N, 8);
+    if (g > 8 * num_sms()) g = 8 * num_sms();
+    k_row_norms<<<g, 256, 0, st>>>(V, N, D, nrm);
+    GDN_CHECK_LAUNCH("k_row_norms");
+    k_gram_topk<<<ceil_div(N, GB_TI), 256, smem, st>>>(V, nrm, N, D, K, idx, nbr, nullptr);
     GDN_CHECK_LAUNCH("k_gram_topk");
     return 0;
 }

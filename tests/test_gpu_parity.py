@@ -278,3 +278,39 @@ def test_graph_follows_the_embedding_under_a_fused_optimizer():
         assert model.learned_graph is a                                   # eval: cached
     want, _ = ops.graph_build(model.embedding.weight, K, use_tensor_cores=0)
     assert torch.equal(a, want)
+
+
+@pytest.mark.parametrize("shape", [(4096, 128, 32), (1500, 128, 17), (2048, 64, 64), (16384, 128, 64)],
+                         ids=["C4", "ragged", "dim64", "C5"])
+def test_tensor_core_graph_engine_is_bit_identical_to_fp32_engine(shape):
+    """The tcgen05 split-precision Gram + exact re-score must reproduce the fp32 FMA engine bit for
+    bit (indices and order), and the auto mode must pick it at these sizes."""
+    from gdn_b200 import ops
+    N, D, K = shape
+    torch.manual_seed(N + K)
+    V = (torch.rand(N, D, device="cuda") * 2 - 1) / D ** 0.5
+    i0, n0 = ops.graph_build(V, K, use_tensor_cores=0)
+    i1, n1 = ops.graph_build(V, K, use_tensor_cores=1)
+    ia, na = ops.graph_build(V, K, use_tensor_cores=-1)
+    assert torch.equal(i0, i1) and torch.equal(n0, n1)
+    assert torch.equal(i0, ia) and torch.equal(n0, na)
+
+
+def test_tensor_core_graph_engine_falls_back_on_ambiguous_rows():
+    """Degenerate embeddings (40 identical sensors, a scaled copy): more exact ties than the candidate
+    slack can hold -> the affected 64-row blocks are recomputed by the exact engine."""
+    from gdn_b200 import ops
+    torch.manual_seed(0)
+    V = (torch.rand(2048, 128, device="cuda") * 2 - 1) / 128 ** 0.5
+    V[100:140] = V[100]
+    V[900] = V[5] * 3.0
+    i0, n0 = ops.graph_build(V, 16, use_tensor_cores=0)
+    i1, n1 = ops.graph_build(V, 16, use_tensor_cores=1)
+    assert torch.equal(i0, i1) and torch.equal(n0, n1)
+
+
+def test_tensor_core_engine_rejects_unsupported_shapes_loudly():
+    from gdn_b200 import ops
+    V = torch.rand(256, 128, device="cuda")
+    with pytest.raises(RuntimeError, match="tcgen05"):
+        ops.graph_build(V, 8, use_tensor_cores=1)
