@@ -212,17 +212,30 @@ k_lin_fwd(const float* __restrict__ A, const float* __restrict__ Wl, const float
 
 // g_out -> g_A[r,w] = sum_d g_out[r,d] Wl[d,w];  partial g_Wl[d,w] += g_out[r,d] A[r,w];
 // partial g_bias[d] += g_out[r,d].   part record: [D*W + D] doubles.
-// dynamic smem: max(row stage, red[8][33][32] floats)
+//
+// A warp stages 32 rows of g_out (coalesced 512-byte rows, all loads in flight) and of A in shared
+// memory, then uses the tile twice with two thread mappings and no shuffles:
+//   (a) lane <-> channels: g_Wl / g_bias accumulate in registers, A rows broadcast;
+//   (b) lane <-> row:      g_A[r, 0:W] = sum_d g[r,d] Wl[d, 0:W], Wl broadcast from shared memory.
+// dynamic smem: Wl [D][WP] | per warp: g tile [32][D+4], A tile [32][WP+4]; reduction scratch aliases it.
 template <int DPL, int WP>
 __global__ void __launch_bounds__(256)
 k_lin_bwd(const float* __restrict__ gout, const float* __restrict__ A, const float* __restrict__ Wl,
           long long n, int W, int D, float* __restrict__ gA, double* __restrict__ part) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    float* sa = RowStage<WP>::tile();
-    float wl[DPL][WP], gwl[DPL][WP], gb[DPL];
-    load_wl<DPL, WP>(Wl, W, lane, wl);
+    constexpr int DT = DPL * 32;              // == D
+    constexpr int GS = DT + 4;                // g tile row stride (floats): conflict-free float4 column reads
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long warp = (long long)blockIdx.x * nw + wid;
+    const long long nwarps = (long long)gridDim.x * nw;
+    float* sWl = reinterpret_cast<float*>(dyn_smem);                       // [DT][WP]
+    float* sG = sWl + DT * WP + (size_t)wid * (32 * GS + RowStage<WP>::WARP_FLOATS);
+    float* sa = sG + 32 * GS;
+    for (int e = threadIdx.x; e < DT * WP; e += blockDim.x) {
+        const int d = e / WP, w = e % WP;
+        sWl[e] = w < W ? Wl[(size_t)d * W + w] : 0.f;
+    }
+    __syncthreads();
+    float gwl[DPL][WP], gb[DPL];
 #pragma unroll
     for (int j = 0; j < DPL; ++j) {
         gb[j] = 0.f;
@@ -232,26 +245,68 @@ k_lin_bwd(const float* __restrict__ gout, const float* __restrict__ A, const flo
     for (long long r0 = warp * 32; r0 < n; r0 += nwarps * 32) {
         const int nb = (int)((n - r0) < 32 ? (n - r0) : 32);
         RowStage<WP>::fill(sa, A + (size_t)r0 * W, (size_t)W, nb, W, lane);
-        for (int rr = 0; rr < nb; ++rr) {
-            const long long r = r0 + rr;
-            float a[WP], go[DPL], pw[WP];
-            RowStage<WP>::get(sa, rr, a);
-            load_chan_vec<DPL>(gout + (size_t)r * D, lane, go);
+        // stage g_out rows: row rr <- 32 lanes x DPL floats, coalesced
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+            float go[DPL];
+            if (rr < nb) load_chan_vec<DPL>(gout + (size_t)(r0 + rr) * D, lane, go);
+            else {
 #pragma unroll
-            for (int w = 0; w < WP; ++w) pw[w] = 0.f;
+                for (int j = 0; j < DPL; ++j) go[j] = 0.f;
+            }
+            store_chan<DPL>(sG + rr * GS, lane, go);
+        }
+        __syncwarp();
+        // (a) lane <-> channels
+#pragma unroll 2
+        for (int rr = 0; rr < nb; ++rr) {
+            float a[WP], go[DPL];
+            RowStage<WP>::get(sa, rr, a);
+            load_chan_vec<DPL>(sG + rr * GS, lane, go);
 #pragma unroll
             for (int j = 0; j < DPL; ++j) {
                 gb[j] += go[j];
 #pragma unroll
-                for (int w = 0; w < WP; ++w) {
-                    pw[w] = fmaf(go[j], wl[j][w], pw[w]);
-                    gwl[j][w] = fmaf(go[j], a[w], gwl[j][w]);
+                for (int w = 0; w < WP; ++w) gwl[j][w] = fmaf(go[j], a[w], gwl[j][w]);
+            }
+        }
+        // (b) lane <-> row
+        {
+            float acc[WP];
+#pragma unroll
+            for (int w = 0; w < WP; ++w) acc[w] = 0.f;
+            const float* grow = sG + lane * GS;
+#pragma unroll 2
+            for (int d4 = 0; d4 < DT / 4; ++d4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(grow + 4 * d4);
+                const float gq[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4* wrow = reinterpret_cast<const float4*>(sWl + (size_t)(4 * d4 + c) * WP);
+#pragma unroll
+                    for (int q = 0; q < WP / 4; ++q) {
+                        const float4 w4 = wrow[q];                                 // broadcast
+                        acc[4 * q] = fmaf(gq[c], w4.x, acc[4 * q]);
+                        acc[4 * q + 1] = fmaf(gq[c], w4.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(gq[c], w4.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(gq[c], w4.w, acc[4 * q + 3]);
+                    }
                 }
             }
-            int widx;
-            const float tot = reduce_scatter<WP>(pw, lane, &widx);
-            if ((lane & ((32 / WP) - 1)) == 0 && widx < W) gA[(size_t)r * W + widx] = tot;
+            if (lane < nb) {
+                float* o = gA + (size_t)(r0 + lane) * W;
+                if ((W & 3) == 0) {
+#pragma unroll
+                    for (int w = 0; w < WP; w += 4)
+                        if (w < W) *reinterpret_cast<float4*>(o + w) = make_float4(acc[w], acc[w + 1], acc[w + 2], acc[w + 3]);
+                } else {
+#pragma unroll
+                    for (int w = 0; w < WP; ++w)
+                        if (w < W) o[w] = acc[w];
+                }
+            }
         }
+        __syncwarp();
     }
     __syncthreads();
     float (*red)[33][32] = reinterpret_cast<float (*)[33][32]>(dyn_smem);
@@ -266,7 +321,7 @@ k_lin_bwd(const float* __restrict__ gout, const float* __restrict__ A, const flo
             const int w = e >> 5, l = e & 31;
             if (w < W || w == 32) {
                 double s = 0.0;
-                for (int q = 0; q < 8; ++q) s += (double)red[q][w][l];
+                for (int q = 0; q < nw; ++q) s += (double)red[q][w][l];
                 const int d = l * DPL + j;
                 if (w == 32) prec[(size_t)D * W + d] = s;
                 else prec[(size_t)d * W + w] = s;
@@ -428,22 +483,36 @@ k_fwd_stats2(HeadArgs h, double* __restrict__ part) {
     cta_reduce_channels<2 * DPL, DPL>(acc, h.D, part + (size_t)blockIdx.x * 2 * h.D, reinterpret_cast<double*>(dyn_smem));
 }
 
+// Dropout keep bits of one row, produced by the lane that owns the row (32 rows of a batch are
+// generated in parallel by the 32 lanes).  Word j holds channel slot j of every lane: bit l <->
+// channel l*DPL + j.  Explicit mask (tests): bit = mask != 0.  Otherwise Philox4x32-10: one call
+// yields eight 16-bit uniforms, keep iff u16 >= round(p * 65536); counter = (row*DPL + j)*4 + q.
 template <int DPL>
-__device__ __forceinline__ void keep_flags(const HeadArgs& h, size_t r, int lane, bool (&keep)[DPL]) {
+__device__ __forceinline__ void gen_keep_words(const HeadArgs& h, size_t r, uint32_t (&words)[DPL]) {
     if (h.mask != nullptr) {
-        float m[DPL];
-        load_chan_vec<DPL>(h.mask + r * h.D, lane, m);
-#pragma unroll
-        for (int j = 0; j < DPL; ++j) keep[j] = m[j] != 0.f;
-    } else {
-        uint4 rnd = make_uint4(0, 0, 0, 0);
+        const float* m = h.mask + r * h.D;
 #pragma unroll
         for (int j = 0; j < DPL; ++j) {
-            const unsigned long long e = (unsigned long long)r * h.D + (unsigned)(lane * DPL + j);
-            const int comp = (int)(e & 3ull);
-            if (j == 0 || comp == 0) rnd = philox4x32_10(e >> 2, h.offset, h.seed);
-            const uint32_t x = comp == 0 ? rnd.x : comp == 1 ? rnd.y : comp == 2 ? rnd.z : rnd.w;
-            keep[j] = u01(x) >= h.p_drop;
+            uint32_t w = 0u;
+            for (int l = 0; l < 32; ++l) w |= (m[l * DPL + j] != 0.f) ? (1u << l) : 0u;
+            words[j] = w;
+        }
+    } else {
+        const uint32_t thr16 = (uint32_t)(h.p_drop * 65536.f + 0.5f);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            uint32_t w = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 rnd = philox4x32_10((unsigned long long)(r * DPL + j) * 4ull + q, h.offset, h.seed);
+                const uint32_t x[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    w |= ((x[c] & 0xffffu) >= thr16 ? 1u : 0u) << (q * 8 + c * 2);
+                    w |= ((x[c] >> 16) >= thr16 ? 1u : 0u) << (q * 8 + c * 2 + 1);
+                }
+            }
+            words[j] = w;
         }
     }
 }
@@ -472,32 +541,21 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
             float my_pred = 0.f;
             uint32_t my_bits[DPL];
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) my_bits[j] = 0u;
+            for (int j = 0; j < DPL; ++j) my_bits[j] = 0xffffffffu;
+            if (drop && lane < nb) gen_keep_words<DPL>(h, (size_t)(b0 + lane) * h.N + i, my_bits);
 #pragma unroll 2
             for (int rr = 0; rr < nb; ++rr) {
-                const size_t r = (size_t)(b0 + rr) * h.N + i;
                 float a[WP], xh1[DPL], y1[DPL];
                 RowStage<WP>::get(sa_, rr, a);
                 re.eval(a, xh1, y1);
-                bool keep[DPL];
-#pragma unroll
-                for (int j = 0; j < DPL; ++j) keep[j] = true;
-                if (drop) {
-                    keep_flags<DPL>(h, r, lane, keep);
-#pragma unroll
-                    for (int j = 0; j < DPL; ++j) {
-                        const uint32_t word = __ballot_sync(0xffffffffu, keep[j]);
-                        if (lane == rr) my_bits[j] = word;
-                    }
-                }
                 float dot = 0.f;
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) {
+                    const uint32_t word = __shfl_sync(0xffffffffu, my_bits[j], rr);
+                    const float kf = drop ? (((word >> lane) & 1u) ? h.scale : 0.f) : 1.f;
                     const float p = fmaxf(y1[j], 0.f) * v[j];
                     const float y2 = fmaf(g2[j], fmaf(p, k2a[j], k2b[j]), be2[j]);
-                    float hm = fmaxf(y2, 0.f);
-                    if (drop) hm = keep[j] ? hm * h.scale : 0.f;
-                    dot = fmaf(hm, wo[j], dot);
+                    dot = fmaf(fmaxf(y2, 0.f) * kf, wo[j], dot);
                 }
                 dot = warp_sum(dot);
                 if (lane == rr) my_pred = dot + bo;
@@ -1021,9 +1079,25 @@ int launch_lin_fwd(const Shape& s, const float* A, const gdn_layer_params* p, fl
 
 int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_layer_params* p, float* gA,
                    double* part, int* nrec, cudaStream_t st) {
-    const int grid = dw_grid(s.n);
-#define CALL(DPLC, WPC) \
-    GDN_LAUNCH_DYN((k_lin_bwd<DPLC, WPC>), grid, dw_smem<WPC>(0, true), st, gout, A, p->lin_weight, s.n, s.W, s.D, gA, part)
+    // warps per CTA: as many as fit the shared-memory tiles
+    int nw = 8;
+    auto bytes = [&](int w) {
+        size_t b = (size_t)s.D * s.WP * 4 + (size_t)w * (32 * (s.D + 4) + 32 * (s.WP + 4)) * 4;
+        const size_t red = (size_t)w * 33 * 32 * 4;
+        return b > red ? b : red;
+    };
+    while (nw > 1 && bytes(nw) > 200 * 1024) nw >>= 1;
+    const size_t smem = bytes(nw);
+    long long g = (s.n + 32LL * nw - 1) / (32LL * nw);
+    if (g > 2 * num_sms()) g = 2 * num_sms();
+    const int grid = (int)(g < 1 ? 1 : g);
+#define CALL(DPLC, WPC)                                                                                          \
+    do {                                                                                                         \
+        cudaError_t e__ = cudaFuncSetAttribute(k_lin_bwd<DPLC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)smem);                                                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, "smem attribute k_lin_bwd");                               \
+        k_lin_bwd<DPLC, WPC><<<grid, nw * 32, smem, st>>>(gout, A, p->lin_weight, s.n, s.W, s.D, gA, part);      \
+    } while (0)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_lin_bwd");

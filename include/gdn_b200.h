@@ -95,7 +95,9 @@ typedef struct gdn_head_grads {
 
 /* Dropout(0.2) (models/GDN.py:114,182).  Either an explicit keep-mask (test hook:
  * values in {0, 1/(1-p)}, layout [B, N, D]) or counter-based Philox4x32-10 keyed by
- * (seed, offset): element (b, i, d) uses counter ((b*N+i)*D + d) / 4, lane % 4. */
+ * (seed, offset): one call yields eight 16-bit uniforms (keep iff u16 >= round(p * 65536));
+ * with DPL = D/32 and d = l*DPL + j, element (b, i, d) uses counter (((b*N+i)*DPL + j)*4 + l/8),
+ * 16-bit field l % 8.  The forward stores the keep bits (1 bit per element) for the backward. */
 typedef struct gdn_dropout {
     const float* mask;   /* NULL -> Philox */
     uint64_t seed;
