@@ -287,6 +287,21 @@ def run_ours(args):
            "h2d_bytes_per_step": int(xs[0].numel() * 4 + ys[0].numel() * 4), "d2h_bytes_per_step": 4,
            "ms_per_step": e2e_ms / args.steps, "last_loss": losses[-1]}
 
+    # ---- the same step captured into a CUDA graph (single GPU): what the launch-bound configs gain
+    graph_info = None
+    if world == 1 and not args.no_extras:
+        from gdn_b200.graphed import GraphedTrainStep
+        torch.manual_seed(5)
+        gmodel = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).to(dev)
+        stepper = GraphedTrainStep(gmodel, (B, N, W), lr=1e-3)
+        for i in range(3):
+            stepper.step(xs[i % nbuf], ys[i % nbuf])
+        gms = timed(lambda i: stepper.step(xs[i % nbuf], ys[i % nbuf]), args.steps)
+        graph_info = {"value": B * args.steps / (sum(gms) / 1e3), "unit": UNIT, "ms_per_step": sum(gms) / args.steps,
+                      "what": "same step (graph build+forward+mse+backward+fused Adam) replayed from one CUDA graph; "
+                              "includes the device copy of the batch into the graph's static buffers"}
+        del stepper, gmodel
+
     # ---- per-kernel breakdown of the train step (separate, profiled steps)
     lib.gdn_profile_enable(1)
     PSTEPS = 3
@@ -306,6 +321,8 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,
     }
+    if graph_info is not None:
+        line["cuda_graph"] = graph_info
     if rank == 0:
         line["clocks"] = clocks
         line["kernels_ms_per_step"] = {k: round(v["ms_per_step"], 5) for k, v in sorted(

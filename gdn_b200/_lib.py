@@ -35,7 +35,8 @@ class HeadGrads(C.Structure):
 
 
 class Dropout(C.Structure):
-    _fields_ = [("mask", c_fp), ("seed", C.c_uint64), ("offset", C.c_uint64), ("p", C.c_float)]
+    _fields_ = [("mask", c_fp), ("seed", C.c_uint64), ("offset", C.c_uint64), ("p", C.c_float),
+                ("offset_dev", c_fp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/gdn_b200.h declares

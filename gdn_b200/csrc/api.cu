@@ -51,6 +51,27 @@ void prof_mark(const char* what) {
     if (g_prof_on) prof_push(what);
 }
 
+cudaError_t ensure_dyn_smem_ptr(const void* kernel, size_t bytes) {
+    // per-kernel high-water mark (keyed by the function pointer, NOT by its type: template
+    // instantiations share a type)
+    static const void* keys[512];
+    static size_t have[512];
+    static int n = 0;
+    int k = 0;
+    for (; k < n; ++k)
+        if (keys[k] == kernel) break;
+    if (k == n) {
+        if (n == 512) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        keys[n] = kernel;
+        have[n] = 0;   // static + dynamic may already exceed the 48 KB default: always opt in once
+        ++n;
+    }
+    if (bytes <= have[k]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have[k] = bytes;
+    return e;
+}
+
 int num_sms() {
     static int cached = 0;
     if (cached == 0) {
@@ -166,6 +187,7 @@ static HeadArgs head_args(const Shape& s, const char* ctx, const CtxLayout& L, c
     a.bits = (uint32_t*)(const_cast<char*>(ctx) + L.bits);
     a.seed = dp ? dp->seed : 0ull;
     a.offset = dp ? dp->offset : 0ull;
+    a.offset_dev = dp ? (const unsigned long long*)dp->offset_dev : nullptr;
     a.p_drop = dp ? dp->p : 0.f;
     a.scale = (dp && dp->p > 0.f && dp->p < 1.f) ? 1.f / (1.f - dp->p) : 1.f;
     a.training = training;

@@ -183,19 +183,18 @@ __global__ void k_attn_alpha(const float* __restrict__ siT, const float* __restr
 
 // ---------------------------------------------------------------------------------------
 // backward: g_A -> g_s_i (store), g_s_j (coalesced RED)
-//   g_alpha[k] = g_A . x[S_k];  g_l = alpha (g_alpha - sum_k alpha g_alpha);
+//   g_alpha[k] = g_A . x[S_k];  g_l = alpha (g_alpha - dot),  dot = sum_k alpha g_alpha;
 //   g_pre = g_l * (pre > 0 ? 1 : 0.2);  g_si = sum_k g_pre;  g_sj[S_k] += g_pre
-// dynamic smem: (blockDim/32) * Kp * 32 floats (g_alpha stash, lane-private columns)
+// dot needs no pass of its own: sum_k alpha_k (g_A . x_k) = g_A . (sum_k alpha_k x_k) = g_A . A, and A
+// is saved by the forward.  One sweep over the edges, no stash, no second exp.
 // ---------------------------------------------------------------------------------------
 template <int WP>
 __global__ void __launch_bounds__(256)
 k_attn_bwd(const float* __restrict__ xT, const float* __restrict__ siT, const float* __restrict__ sjT,
            const float* __restrict__ mT, const float* __restrict__ linvT,
-           const int32_t* __restrict__ nbr, const float* __restrict__ gA,
+           const int32_t* __restrict__ nbr, const float* __restrict__ gA, const float* __restrict__ A,
            int B, int N, int W, int Kp, int Bs, float* __restrict__ gsiT, float* __restrict__ gsjT) {
-    extern __shared__ float stash_all[];
     const int lane = threadIdx.x & 31;
-    float* stash = stash_all + (size_t)(threadIdx.x >> 5) * Kp * 32 + lane;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int chunks = Bs >> 5;
@@ -212,19 +211,24 @@ k_attn_bwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
         const float si = siT[(size_t)i * Bs + b];
         const float m = mT[(size_t)i * Bs + b], linv = linvT[(size_t)i * Bs + b];
         float g[WP];
-        const float* grow = gA + ((size_t)(ok ? b : 0) * N + i) * W;
+        const size_t roff = ((size_t)(ok ? b : 0) * N + i) * W;
+        float dot = 0.f;
 #pragma unroll
-        for (int w = 0; w < WP; ++w) g[w] = (ok && w < W) ? grow[w] : 0.f;
+        for (int w = 0; w < WP; ++w) {
+            g[w] = (ok && w < W) ? gA[roff + w] : 0.f;
+            if (ok && w < W) dot = fmaf(g[w], A[roff + w], dot);
+        }
         int deg = 0;
         for (int k = 0; k < Kp; ++k) {
             if (__ldg(nb + k) < 0) break;
             ++deg;
         }
-        float dot = 0.f;
+        float gsi = 0.f;
 #pragma unroll 4
         for (int k = 0; k < deg; ++k) {
             const unsigned src = (unsigned)__ldg(nb + k);
-            const float a = expf(leaky(si + sjb[src * (unsigned)Bs]) - m) * linv;
+            const float pre = si + sjb[src * (unsigned)Bs];
+            const float a = expf(leaky(pre) - m) * linv;
             const float* xs = xb + src * xstride;
             float ga0 = 0.f, ga1 = 0.f;
 #pragma unroll
@@ -232,20 +236,16 @@ k_attn_bwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
                 ga0 = fmaf(g[w], xs[w * 32], ga0);
                 ga1 = fmaf(g[w + 1], xs[(w + 1) * 32], ga1);
             }
-            const float ga = ga0 + ga1;
-            stash[k * 32] = ga;
-            dot = fmaf(a, ga, dot);
-        }
-        float gsi = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < deg; ++k) {
-            const unsigned src = (unsigned)__ldg(nb + k);
-            const float pre = si + sjb[src * (unsigned)Bs];
-            const float a = expf(leaky(pre) - m) * linv;
-            const float gl = a * (stash[k * 32] - dot);
+            const float gl = a * ((ga0 + ga1) - dot);
             const float gp = pre > 0.f ? gl : GDN_NEG_SLOPE * gl;
             gsi += gp;
-            if (ok) atomicAdd(gsjb + src * (unsigned)Bs, gp);
+            // the L2 atomic units are the limiter of this kernel (one op per element): pack four windows
+            // into one red.global.add.v4.f32 (padding lanes carry exact zeros)
+            const float v1 = __shfl_down_sync(0xffffffffu, gp, 1);
+            const float v2 = __shfl_down_sync(0xffffffffu, gp, 2);
+            const float v3 = __shfl_down_sync(0xffffffffu, gp, 3);
+            if ((lane & 3) == 0)
+                atomicAdd(reinterpret_cast<float4*>(gsjb + src * (unsigned)Bs), make_float4(gp, v1, v2, v3));
         }
         gsiT[(size_t)i * Bs + b] = ok ? gsi : 0.f;
     }
@@ -392,20 +392,10 @@ int launch_attn_bwd(const Shape& s, const int32_t* nbr, const char* ctx, const C
     const float* linvT = (const float*)(ctx + L.linvT);
     cudaError_t e = cudaMemsetAsync(gsjT, 0, (size_t)s.N * s.Bs * sizeof(float), st);
     if (e != cudaSuccess) return cuda_fail(e, "memset g_sj");
-    int warps = 8;
-    while (warps > 1 && (size_t)warps * s.Kp * 32 * sizeof(float) > 96 * 1024) warps >>= 1;
-    const size_t smem = (size_t)warps * s.Kp * 32 * sizeof(float);
-    GDN_CHECK_ARG(smem <= 200 * 1024, "topk=%d too large for the attention backward stash", s.K);
-    const int grid = grid_for_warps(tasks, warps, 32 * num_sms());
+    const int grid = grid_for_warps(tasks, 8, 32 * num_sms());
+    const float* Arows = (const float*)(ctx + L.A);
 #define GDN_LAUNCH_AB(WPV)                                                                              \
-    do {                                                                                                \
-        if (smem > 48 * 1024) {                                                                         \
-            e = cudaFuncSetAttribute(k_attn_bwd<WPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return cuda_fail(e, "smem attr k_attn_bwd");                          \
-        }                                                                                               \
-        k_attn_bwd<WPV><<<grid, warps * 32, smem, st>>>(xT, siT, sjT, mT, linvT, nbr, gA, s.B, s.N, s.W, \
-                                                         s.Kp, s.Bs, gsiT, gsjT);                       \
-    } while (0)
+    k_attn_bwd<WPV><<<grid, 256, 0, st>>>(xT, siT, sjT, mT, linvT, nbr, gA, Arows, s.B, s.N, s.W, s.Kp, s.Bs, gsiT, gsjT)
     if (s.WP == 8) GDN_LAUNCH_AB(8);
     else if (s.WP == 16) GDN_LAUNCH_AB(16);
     else GDN_LAUNCH_AB(32);

@@ -40,6 +40,14 @@ static inline int    round_up32(int v) { return (v + 31) & ~31; }
 
 int num_sms();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the request grows: keeps the call out of
+// steady-state launches (and out of CUDA-graph captures after the warm-up iterations)
+cudaError_t ensure_dyn_smem_ptr(const void* kernel, size_t bytes);
+template <typename K>
+static inline cudaError_t ensure_dyn_smem(K kernel, size_t bytes) {
+    return ensure_dyn_smem_ptr(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 // ---------------------------------------------------------------------------------------
 // ctx / ws layouts (byte offsets; every region 256-byte aligned)
 // ---------------------------------------------------------------------------------------

@@ -499,12 +499,13 @@ __device__ __forceinline__ void gen_keep_words(const HeadArgs& h, size_t r, uint
         }
     } else {
         const uint32_t thr16 = (uint32_t)(h.p_drop * 65536.f + 0.5f);
+        const unsigned long long offset = h.offset + (h.offset_dev ? *h.offset_dev : 0ull);
 #pragma unroll
         for (int j = 0; j < DPL; ++j) {
             uint32_t w = 0u;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint4 rnd = philox4x32_10((unsigned long long)(r * DPL + j) * 4ull + q, h.offset, h.seed);
+                const uint4 rnd = philox4x32_10((unsigned long long)(r * DPL + j) * 4ull + q, offset, h.seed);
                 const uint32_t x[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -1052,8 +1053,8 @@ static size_t dw_smem(int nv_double, bool red33) {
 #define GDN_LAUNCH_DYN(KERNEL, GRID, SMEM, ST, ...)                                                     \
     do {                                                                                               \
         const size_t sm__ = (SMEM);                                                                    \
-        if (sm__ > 48 * 1024) {                                                                        \
-            cudaError_t e__ = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm__); \
+        {                                                                                              \
+            cudaError_t e__ = ensure_dyn_smem(KERNEL, sm__);                                           \
             if (e__ != cudaSuccess) return cuda_fail(e__, "smem attribute");                           \
         }                                                                                              \
         KERNEL<<<GRID, 256, sm__, ST>>>(__VA_ARGS__);                                                  \
@@ -1093,8 +1094,7 @@ int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_
     const int grid = (int)(g < 1 ? 1 : g);
 #define CALL(DPLC, WPC)                                                                                          \
     do {                                                                                                         \
-        cudaError_t e__ = cudaFuncSetAttribute(k_lin_bwd<DPLC, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                               (int)smem);                                                       \
+        cudaError_t e__ = ensure_dyn_smem(k_lin_bwd<DPLC, WPC>, smem);                                           \
         if (e__ != cudaSuccess) return cuda_fail(e__, "smem attribute k_lin_bwd");                               \
         k_lin_bwd<DPLC, WPC><<<grid, nw * 32, smem, st>>>(gout, A, p->lin_weight, s.n, s.W, s.D, gA, part);      \
     } while (0)

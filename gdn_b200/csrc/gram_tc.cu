@@ -521,7 +521,7 @@ int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* n
     const size_t smem = 1024 + (size_t)2 * KB * TC_BM * 128 + (size_t)TC_STAGES * 2 * KB * TC_BN * 128 +
                         (size_t)2 * 17 * TC_BM * sizeof(float) + (4 + 2 * TC_STAGES + 4) * 8 + 16;
     GDN_CHECK_ARG(smem <= 227 * 1024, "gram_tc: %zu bytes of shared memory needed", smem);
-    e = cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem(k_gram_tc, smem);
     if (e != cudaSuccess) return cuda_fail(e, "smem attr k_gram_tc");
     static int dbg = -1;
     if (dbg < 0) { const char* e_ = getenv("GDN_TC_DBG"); dbg = e_ ? atoi(e_) : 0; }

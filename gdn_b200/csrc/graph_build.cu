@@ -206,7 +206,7 @@ int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_
                   "graph_build: the tcgen05 engine needs N >= 1024, dim 64 or 128, topk <= 72 (N=%d D=%d K=%d)", N, D, K);
     const size_t smem = (size_t)GB_TI * K * (sizeof(float) + sizeof(int));
     {
-        cudaError_t e = cudaFuncSetAttribute(k_gram_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_dyn_smem(k_gram_topk, smem);
         if (e != cudaSuccess) return cuda_fail(e, "smem attr k_gram_topk");
     }
     if (use_tc > 0 || (use_tc < 0 && tc_ok)) {

@@ -16,6 +16,7 @@ struct HeadArgs {
     const float* mask;
     uint32_t* bits;
     unsigned long long seed, offset;
+    const unsigned long long* offset_dev;   // optional device-side addend to `offset` (CUDA-graph replays)
     float p_drop, scale;
     int training;
 };

@@ -118,6 +118,18 @@ class GraphLayerBatchedFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------- fused GDN
+_dropout_counter = None
+
+
+def set_dropout_counter(counter):
+    """Device-side int64 counter added to the Philox offset when the dropout kernel RUNS (not when it is
+    launched): a captured CUDA graph that bumps the counter draws a fresh mask on every replay."""
+    global _dropout_counter
+    if counter is not None and (counter.dtype != torch.int64 or not counter.is_cuda):
+        raise RuntimeError("dropout counter must be a CUDA int64 tensor")
+    _dropout_counter = counter
+
+
 class _DropState:
     """Philox (seed, offset) bookkeeping: the seed follows torch.manual_seed, the offset
     advances by the number of 4-wide counters a forward consumes."""
@@ -172,7 +184,9 @@ class FusedGDNFn(torch.autograd.Function):
         seed, offset = (0, 0)
         if training and drop_p > 0 and mask_c is None:
             seed, offset = _DropState.next(B * N * D)
-        dp = Dropout(mask_c.data_ptr() if mask_c is not None else None, seed, offset, float(drop_p))
+        ctr = _dropout_counter if (_dropout_counter is not None and _dropout_counter.device == dev) else None
+        dp = Dropout(mask_c.data_ptr() if mask_c is not None else None, seed, offset, float(drop_p),
+                     ctr.data_ptr() if ctr is not None else None)
         nb_ctx = lib.gdn_fused_ctx_bytes(C.byref(dims))
         if nb_ctx == 0:
             check(-1, "gdn_fused_ctx_bytes")
@@ -210,7 +224,7 @@ class FusedGDNFn(torch.autograd.Function):
                         BN(ht[2].data_ptr(), ht[3].data_ptr(), rm2.data_ptr(), rv2.data_ptr(), None),
                         ht[4].data_ptr(), ht[5].data_ptr())
         seed, offset, p = ctx.drop
-        dp = Dropout(None, seed, offset, p)
+        dp = Dropout(None, seed, offset, p, None)
         g_layer = [torch.empty_like(t) for t in lt]
         g_V = torch.empty_like(Vc)
         g_head = [torch.empty_like(t) for t in ht]

@@ -103,6 +103,8 @@ typedef struct gdn_dropout {
     uint64_t seed;
     uint64_t offset;
     float p;             /* 0 disables dropout */
+    const uint64_t* offset_dev; /* optional DEVICE counter added to `offset` when the kernel runs: lets a
+                                   captured CUDA graph draw a fresh mask on every replay (may be NULL) */
 } gdn_dropout;
 
 int         gdn_version(void);

@@ -314,3 +314,49 @@ def test_tensor_core_engine_rejects_unsupported_shapes_loudly():
     V = torch.rand(256, 128, device="cuda")
     with pytest.raises(RuntimeError, match="tcgen05"):
         ops.graph_build(V, 8, use_tensor_cores=1)
+
+
+def test_cuda_graph_train_step_matches_eager_steps():
+    """gdn_b200.graphed.GraphedTrainStep: the captured step (graph build + forward + MSE + backward +
+    fused Adam) replays to the same losses and weights as eager steps (dropout off for comparability),
+    and with dropout on every replay draws a new mask."""
+    from gdn_b200.graphed import GraphedTrainStep
+    from gdn_b200.models.GDN import GDN
+    N, W, D, K, B = 51, 5, 64, 15, 32
+    torch.manual_seed(11)
+    xs = [torch.rand(B, N, W, device="cuda") for _ in range(4)]
+    ys = [torch.rand(B, N, device="cuda") for _ in range(4)]
+
+    def make():
+        torch.manual_seed(3)
+        m = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()
+        m.dp.p = 0.0
+        return m
+
+    eager = make()
+    opt = torch.optim.Adam(eager.parameters(), lr=1e-3)
+    want = []
+    for x, y in zip(xs, ys):
+        opt.zero_grad()
+        loss = torch.nn.functional.mse_loss(eager(x, None), y)
+        loss.backward()
+        opt.step()
+        want.append(loss.item())
+    graphed = make()
+    stepper = GraphedTrainStep(graphed, (B, N, W), lr=1e-3)
+    got = [stepper.step(x, y).item() for x, y in zip(xs, ys)]
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 2e-4 * abs(b), (got, want)
+    for (k, p), (_, q) in zip(graphed.state_dict().items(), eager.state_dict().items()):
+        if k.endswith("gnn.bias"):      # its gradient is analytically 0: Adam turns rounding noise into +-lr steps
+            continue
+        # ... and that +-lr noise on gnn.bias shifts BatchNorm-1's running mean by up to steps*lr
+        assert normwise(p.cpu(), q.cpu()) < (5e-2 if "running_mean" in k else 1e-3), k
+    assert int(stepper.counter.item()) == 4
+    # dropout on: same input twice -> different masks -> different losses even with lr = 0
+    drop = make()
+    drop.dp.p = 0.2
+    st2 = GraphedTrainStep(drop, (B, N, W), lr=0.0)
+    l1 = st2.step(xs[0], ys[0]).item()
+    l2 = st2.step(xs[0], ys[0]).item()
+    assert l1 != l2
