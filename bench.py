@@ -256,25 +256,28 @@ def run_ours(args):
         total_ms = float(t.item())
     value = world * B * args.steps / (total_ms / 1e3)
 
-    # ---- end to end: host buffers -> H2D -> step -> loss back on the host, every step
-    hx = [x.cpu().pin_memory() for x in xs]
+    # ---- end to end: host buffers -> H2D -> step -> loss back on the host, every step.
+    # The feed is the product's: gdn_b200.data.Prefetcher (pinned staging, copy stream, one batch in
+    # flight) around a plain iterable of CPU batches, i.e. what wraps the reference's DataLoader.
+    from gdn_b200.data import Prefetcher
+    hx = [x.cpu().pin_memory() for x in xs]              # as DataLoader(pin_memory=True) hands them over
     hy = [y.cpu().pin_memory() for y in ys]
-    dx, dy = torch.empty_like(xs[0]), torch.empty_like(ys[0])
     losses = []
 
-    def e2e_step(i):
-        dx.copy_(hx[i % nbuf], non_blocking=True)
-        dy.copy_(hy[i % nbuf], non_blocking=True)
-        losses.append(trainer.step(dx, dy).item())           # D2H + sync, as train.py:76
+    def host_batches(count):
+        for i in range(count):
+            yield hx[i % nbuf], hy[i % nbuf]
 
-    for i in range(2):
-        e2e_step(i)
+    def e2e_run(count):
+        for bx, by in Prefetcher(host_batches(count), dev, skip=()):
+            losses.append(trainer.step(bx, by).item())       # D2H + sync every step, as train.py:76
+
+    e2e_run(3)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_run(args.steps)
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)

@@ -360,3 +360,20 @@ def test_cuda_graph_train_step_matches_eager_steps():
     l1 = st2.step(xs[0], ys[0]).item()
     l2 = st2.step(xs[0], ys[0]).item()
     assert l1 != l2
+
+
+def test_prefetcher_feeds_identical_batches_in_order():
+    """gdn_b200.data.Prefetcher: same tensors, same order as a blocking .to(device) loop; the skipped
+    position (the reference's unused edge_index) is passed through untouched."""
+    from gdn_b200.data import Prefetcher
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.rand(8, 27, 5, generator=g, dtype=torch.float64), torch.rand(8, 27, generator=g),
+                torch.zeros(8), torch.arange(10).view(2, 5)) for _ in range(5)]
+    seen = 0
+    for got, want in zip(Prefetcher(batches, "cuda"), batches):
+        assert got[0].is_cuda and got[0].dtype == torch.float32
+        assert torch.equal(got[0].cpu(), want[0].float()) and torch.equal(got[1].cpu(), want[1])
+        assert got[3] is want[3]
+        seen += 1
+    assert seen == 5 and len(Prefetcher(batches, "cuda")) == 5
+    assert list(Prefetcher([], "cuda")) == []
