@@ -269,7 +269,7 @@ def run_ours(args):
             yield hx[i % nbuf], hy[i % nbuf]
 
     def e2e_run(count):
-        for bx, by in Prefetcher(host_batches(count), dev, skip=()):
+        for bx, by in Prefetcher(host_batches(count), dev, skip=(), reuse_buffers=True):
             losses.append(trainer.step(bx, by).item())       # D2H + sync every step, as train.py:76
 
     e2e_run(3)

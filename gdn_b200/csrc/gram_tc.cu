@@ -152,7 +152,7 @@ __global__ void k_normalise_split(const float* __restrict__ V, int N, int D, flo
 __global__ void __launch_bounds__(256, 1)
 k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
           int N, int KB, int L, int C, float* __restrict__ bufv, int* __restrict__ bufj, int* __restrict__ rowcnt,
-          int* __restrict__ err, int dbg) {
+          const float* __restrict__ hint, float margin, int* __restrict__ flags, int* __restrict__ err, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B atoms: 1024-byte aligned
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -251,7 +251,16 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
         float* pv = p_vals + row;                    // staging slot q of row r at [q * 128 + r]; slot 16 = trash
         int* pj = p_idxs + row;
         int cnt = 0;
+        // Warm start: the caller may pass last step's K-th cosine per row.  The embedding moves by one
+        // optimiser step between graph builds, so (hint - margin) is a valid admission threshold for
+        // nearly every row and the sweep appends ~L + margin*density entries instead of ~L ln(N/L): no
+        // compaction before the final one.  A row that ends with fewer than L entries had a stale hint:
+        // its block is flagged and recomputed by the exact engine.
         float thr = -INFINITY;
+        if (hint != nullptr && m0 + row < N) {
+            const float hv = hint[m0 + row];
+            if (hv == hv && hv > -2.f) thr = hv - margin;
+        }
         constexpr int NE = TC_MAXC / 32;
         // order-preserving float <-> unsigned key
         auto to_key = [](float f) -> unsigned {
@@ -369,7 +378,10 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
                 }
             }
         }
-        if (ok && m0 + row < N) rowcnt[m0 + row] = cnt;
+        if (ok && m0 + row < N) {
+            rowcnt[m0 + row] = cnt;
+            if (cnt < L) flags[(m0 + row) / 64] = 1;                 // stale hint: exact fix-up
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -385,6 +397,7 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
 __global__ void __launch_bounds__(256)
 k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int D, int K, int L, int C,
           const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ rowcnt,
+          float* __restrict__ kth_out,
           int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, int* __restrict__ block_flags) {
     __shared__ float s_cos[8][TC_MAXL];
     __shared__ int s_j[8][TC_MAXL];
@@ -395,6 +408,8 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int
     const float* vi = V + (size_t)i * D;
     const float ni = nrm[i];
     const int have = rowcnt[i];
+    for (int k = lane; k < K; k += 32) s_out[wid][k] = i;     // placeholder if the row is short (it is flagged)
+    __syncwarp();
     float amin = INFINITY;
     for (int l = lane; l < L; l += 32) {
         const int j = l < have ? cand_idx[(size_t)i * C + l] : -1;
@@ -436,6 +451,7 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int
             rank += (cq > c || (cq == c && jq < j)) ? 1 : 0;
         }
         if (j >= 0 && rank < K) s_out[wid][rank] = j;
+        if (j >= 0 && rank == K - 1 && kth_out != nullptr) kth_out[i] = c;
     }
     __syncwarp();
     if (idx_out != nullptr)
@@ -484,7 +500,7 @@ size_t gram_tc_ws_bytes(int N, int D, int K) {
 }
 
 int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, cudaStream_t st,
-                   float** nrm_out, int** flags_out) {
+                   float* kth, float margin, float** nrm_out, int** flags_out) {
     const int L = K + TC_SLACK, C = TC_MAXC, KB = D / TC_BK;
     const size_t Npad = (size_t)ceil_div(N, TC_BM) * TC_BM;
     char* p = (char*)ws;
@@ -525,9 +541,10 @@ int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* n
     if (e != cudaSuccess) return cuda_fail(e, "smem attr k_gram_tc");
     static int dbg = -1;
     if (dbg < 0) { const char* e_ = getenv("GDN_TC_DBG"); dbg = e_ ? atoi(e_) : 0; }
-    k_gram_tc<<<ceil_div(N, TC_BM), 256, smem, st>>>(tm_hi, tm_lo, N, KB, L, C, bufv, bufj, rowcnt, err, dbg);
+    k_gram_tc<<<ceil_div(N, TC_BM), 256, smem, st>>>(tm_hi, tm_lo, N, KB, L, C, bufv, bufj, rowcnt, kth, margin, flags,
+                                                     err, dbg);
     GDN_CHECK_LAUNCH("k_gram_tc");
-    k_rescore<<<ceil_div(N, 8), 256, 0, st>>>(V, nrm, N, D, K, L, C, bufv, bufj, rowcnt, idx, nbr, flags);
+    k_rescore<<<ceil_div(N, 8), 256, 0, st>>>(V, nrm, N, D, K, L, C, bufv, bufj, rowcnt, kth, idx, nbr, flags);
     GDN_CHECK_LAUNCH("k_rescore");
     *nrm_out = nrm;
     *flags_out = flags;

@@ -76,7 +76,8 @@ __device__ __forceinline__ void list_insert(float* vals, int* idxs, int* cnt_p, 
 // dynamic smem: lists  vals[GB_TI][K] (float), idxs[GB_TI][K] (int)
 __global__ void __launch_bounds__(256)
 k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, int D, int K,
-            int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, const int* __restrict__ block_flags) {
+            int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, const int* __restrict__ block_flags,
+            float* __restrict__ kth_out) {
     if (block_flags != nullptr && block_flags[blockIdx.x] == 0) return;   // fix-up mode: flagged blocks only
     __shared__ float As[GB_TI][GB_DC + 1];
     __shared__ float Bs[GB_TJ][GB_DC + 1];
@@ -169,6 +170,7 @@ k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, i
         const int cnt = cnts[r];
         if (idx_out != nullptr)
             for (int k = lane; k < K; k += 32) idx_out[(size_t)gi * K + k] = k < cnt ? (int64_t)idxs[k] : (int64_t)gi;
+        if (kth_out != nullptr && lane == 0) kth_out[gi] = cnt >= K ? lvals[(size_t)r * K + K - 1] : -INFINITY;
         if (nbr_out != nullptr && lane == 0) {
             int32_t* nb = nbr_out + (size_t)gi * (K + 1);
             int o = 0;
@@ -186,7 +188,7 @@ k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, i
 bool gram_tc_supported(int N, int D, int K);
 size_t gram_tc_ws_bytes(int N, int D, int K);
 int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, cudaStream_t st,
-                   float** nrm_out, int** flags_out);
+                   float* kth, float margin, float** nrm_out, int** flags_out);
 
 size_t graph_build_ws_bytes(int N, int D, int K) {
     size_t b = align_up((size_t)N * sizeof(float), 256);
@@ -198,7 +200,7 @@ size_t graph_build_ws_bytes(int N, int D, int K) {
 }
 
 int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, size_t ws_bytes,
-                       int use_tc, cudaStream_t st) {
+                       int use_tc, float* kth, float margin, cudaStream_t st) {
     GDN_CHECK_ARG(K <= GB_MAXK, "topk K=%d unsupported (max %d)", K, GB_MAXK);
     GDN_CHECK_ARG(ws != nullptr && ws_bytes >= graph_build_ws_bytes(N, D, K), "graph_build: workspace too small");
     const bool tc_ok = gram_tc_supported(N, D, K);
@@ -212,9 +214,9 @@ int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_
     if (use_tc > 0 || (use_tc < 0 && tc_ok)) {
         float* nrm = nullptr;
         int* flags = nullptr;
-        if (int rc = launch_gram_tc(V, N, D, K, idx, nbr, ws, st, &nrm, &flags)) return rc;
+        if (int rc = launch_gram_tc(V, N, D, K, idx, nbr, ws, st, kth, margin, &nrm, &flags)) return rc;
         // exact fix-up of the (normally zero) 64-row blocks whose candidate window was ambiguous
-        k_gram_topk<<<ceil_div(N, GB_TI), 256, smem, st>>>(V, nrm, N, D, K, idx, nbr, flags);
+        k_gram_topk<<<ceil_div(N, GB_TI), 256, smem, st>>>(V, nrm, N, D, K, idx, nbr, flags, kth);
         GDN_CHECK_LAUNCH("k_gram_topk_fixup");
         return 0;
     }
@@ -223,7 +225,7 @@ int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_
     if (g > 8 * num_sms()) g = 8 * num_sms();
     k_row_norms<<<g, 256, 0, st>>>(V, N, D, nrm);
     GDN_CHECK_LAUNCH("k_row_norms");
-    k_gram_topk<<<ceil_div(N, GB_TI), 256, smem, st>>>(V, nrm, N, D, K, idx, nbr, nullptr);
+    k_gram_topk<<<ceil_div(N, GB_TI), 256, smem, st>>>(V, nrm, N, D, K, idx, nbr, nullptr, kth);
     GDN_CHECK_LAUNCH("k_gram_topk");
     return 0;
 }

@@ -11,15 +11,21 @@ import torch
 
 
 class Prefetcher:
-    def __init__(self, batches, device, skip=(3,), dtype=torch.float32):
+    def __init__(self, batches, device, skip=(3,), dtype=torch.float32, reuse_buffers=False):
+        """reuse_buffers=True copies into two persistent device buffers per tensor position (no allocator
+        traffic); a yielded batch is then only valid until the NEXT-BUT-ONE batch is requested -- right
+        for train.py's loop, wrong for a consumer that keeps aliases of its inputs (test.py:55-57 keeps the
+        first `y`), hence off by default."""
         self.batches = batches
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("Prefetcher feeds a CUDA device (gdn_b200 has no CPU path)")
         self.skip = set(skip)
         self.dtype = dtype
+        self.reuse = bool(reuse_buffers)
         self.stream = torch.cuda.Stream(device=self.device)
         self._pinned = {}
+        self._devbuf = {}
 
     def __len__(self):
         return len(self.batches)
@@ -40,22 +46,39 @@ class Prefetcher:
         buf.copy_(t)
         return buf
 
-    def _issue(self, slot, batch):
+    def _to_device(self, slot, pos, h):
+        if h.is_cuda:
+            return h
+        if not self.reuse:
+            return h.to(self.device, non_blocking=True)
+        key = (slot, pos, tuple(h.shape), h.dtype)
+        buf = self._devbuf.get(key)
+        if buf is None:
+            buf = torch.empty(h.shape, dtype=h.dtype, device=self.device)
+            self._devbuf[key] = buf
+        buf.copy_(h, non_blocking=True)
+        return buf
+
+    def _issue(self, slot, batch, after=None):
         if torch.is_tensor(batch):
             batch = (batch,)
         out = []
         with torch.cuda.stream(self.stream):
+            if after is not None:
+                self.stream.wait_event(after)          # the consumer's work on this slot's previous batch
             for pos, t in enumerate(batch):
                 if pos in self.skip or not torch.is_tensor(t):
                     out.append(t)
                 else:
-                    out.append(self._stage(slot, pos, t).to(self.device, non_blocking=True))
+                    out.append(self._to_device(slot, pos, self._stage(slot, pos, t)))
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return out, ev
 
     def __iter__(self):
         it = iter(self.batches)
+        cur_stream = torch.cuda.current_stream(self.device)
+        done = [None, None]
         slot = 0
         try:
             nxt = self._issue(slot, next(it))
@@ -63,13 +86,18 @@ class Prefetcher:
             return
         while nxt is not None:
             cur, ev = nxt
-            slot ^= 1
+            other = slot ^ 1
             try:
-                nxt = self._issue(slot, next(it))      # next batch's copy overlaps this batch's compute
+                nxt = self._issue(other, next(it), done[other])   # overlaps this batch's compute
             except StopIteration:
                 nxt = None
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            for t in cur:
-                if torch.is_tensor(t) and t.is_cuda:
-                    t.record_stream(torch.cuda.current_stream(self.device))
+            cur_stream.wait_event(ev)
+            if not self.reuse:
+                for t in cur:
+                    if torch.is_tensor(t) and t.is_cuda:
+                        t.record_stream(cur_stream)
             yield tuple(cur)
+            if self.reuse:
+                done[slot] = torch.cuda.Event()
+                done[slot].record(cur_stream)
+            slot = other

@@ -121,6 +121,8 @@ class GDN(nn.Module):
         self._graph_cache = None          # (key, idx, nbr): reused while embedding.weight is unchanged
         self._dropout_mask = None         # test hook: explicit keep mask [B, N, D] in {0, 1/(1-p)}
         self.use_tensor_cores = -1        # graph builder engine: -1 auto, 0 fp32 FMA, 1 tcgen05
+        self._kth = None                  # per-row K-th cosine of the last graph build (warm-start hint)
+        self.graph_margin = 0.03          # admission slack below that hint
 
     def init_params(self):
         nn.init.kaiming_uniform_(self.embedding.weight, a=math.sqrt(5))
@@ -139,7 +141,12 @@ class GDN(nn.Module):
         w = self.embedding.weight
         key = (w.data_ptr(), w._version, int(self.topk), int(self.use_tensor_cores), str(w.device))
         if self.training or self._graph_cache is None or self._graph_cache[0] != key:
-            idx, nbr = ops.graph_build(w, self.topk, use_tensor_cores=self.use_tensor_cores)
+            if self._kth is None or self._kth.device != w.device or self._kth.numel() != w.shape[0]:
+                self._kth = torch.full((w.shape[0],), float("-inf"), dtype=torch.float32, device=w.device)
+            # warm start: last build's K-th cosine per row (the embedding moves one optimiser step between
+            # builds); purely an accelerator -- stale hints are detected and recomputed exactly
+            idx, nbr = ops.graph_build(w, self.topk, use_tensor_cores=self.use_tensor_cores, kth=self._kth,
+                                       margin=self.graph_margin)
             self._graph_cache = None if self.training else (key, idx, nbr)
             return idx, nbr
         return self._graph_cache[1], self._graph_cache[2]

@@ -41,8 +41,12 @@ def make_dims(B, N, W, D, K):
 
 
 # ----------------------------------------------------------------------------- graph
-def graph_build(V, topk, use_tensor_cores=-1, want_idx=True):
-    """models/GDN.py:143-159 -> (learned_graph [N,K] int64, nbr [N,K+1] int32)."""
+def graph_build(V, topk, use_tensor_cores=-1, want_idx=True, kth=None, margin=0.03):
+    """models/GDN.py:143-159 -> (learned_graph [N,K] int64, nbr [N,K+1] int32).
+
+    kth: optional float32 [N] CUDA tensor, in/out: the K-th largest cosine of every row from the previous
+    build (fill with -inf for "no hint"); warm-starts the tensor-core engine's admission threshold and
+    receives this build's values.  The result never depends on the hint."""
     _need_cuda(V, "embedding.weight")
     lib = _lib.load()
     Vc = _f32c(V)
@@ -54,8 +58,15 @@ def graph_build(V, topk, use_tensor_cores=-1, want_idx=True):
     nbr = torch.empty((N, K + 1), dtype=torch.int32, device=Vc.device)
     nb = lib.gdn_graph_build_ws_bytes(N, D, K)
     ws = _blob(nb, Vc.device)
-    check(lib.gdn_graph_build(ptr(Vc), N, D, K, ptr(idx), ptr(nbr), ptr(ws), ws.numel(), int(use_tensor_cores),
-                              _stream()), "gdn_graph_build")
+    if kth is None:
+        check(lib.gdn_graph_build(ptr(Vc), N, D, K, ptr(idx), ptr(nbr), ptr(ws), ws.numel(), int(use_tensor_cores),
+                                  _stream()), "gdn_graph_build")
+    else:
+        if kth.dtype != torch.float32 or kth.device != Vc.device or kth.numel() != N or not kth.is_contiguous():
+            raise RuntimeError("kth must be a contiguous float32 [N] tensor on the embedding's device")
+        check(lib.gdn_graph_build_warm(ptr(Vc), N, D, K, ptr(idx), ptr(nbr), ptr(ws), ws.numel(),
+                                       int(use_tensor_cores), ptr(kth), float(margin), _stream()),
+              "gdn_graph_build_warm")
     return idx, nbr
 
 

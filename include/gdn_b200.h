@@ -5,7 +5,7 @@
  * of its own.  The entry points below are what a binding for this path replaces, one
  * per reference call site (file:line under the reference tree):
  *
- *   gdn_graph_build        models/GDN.py:143-159   cosine Gram + row-wise top-k
+ *   gdn_graph_build(_warm) models/GDN.py:143-159   cosine Gram + row-wise top-k
  *   gdn_graphlayer_fwd     models/graph_layer.py:53-117 (+ PyG propagate/softmax) on the
  *                          window-shared top-k graph built by models/GDN.py:161-165
  *   gdn_graphlayer_bwd     autograd of the above (train.py:72)
@@ -126,6 +126,15 @@ int gdn_profile_collect(char* buf, size_t buf_bytes);
 size_t gdn_graph_build_ws_bytes(int N, int D, int K);
 int    gdn_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr,
                        void* ws, size_t ws_bytes, int use_tensor_cores, void* stream);
+
+/* Same, warm-started: kth [N] float (in/out).  In: the K-th largest cosine of every row from the
+ * PREVIOUS build (anything <= -2 or NaN = no hint); the tcgen05 engine admits only values above
+ * kth[i] - margin, which removes almost all selection work when the embedding moved by one optimiser
+ * step.  Rows whose hint turns out stale are recomputed exactly, so the result never depends on the
+ * hint.  Out: this build's K-th largest cosine per row. */
+int    gdn_graph_build_warm(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr,
+                            void* ws, size_t ws_bytes, int use_tensor_cores, float* kth, float margin,
+                            void* stream);
 
 /* ---- a3/a4: GraphLayer on the window-shared graph ------------------------------------
  * x [B, N, W], V [N, D], nbr [N, K+1] -> out [B*N, D]

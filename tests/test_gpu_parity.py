@@ -377,3 +377,27 @@ def test_prefetcher_feeds_identical_batches_in_order():
         seen += 1
     assert seen == 5 and len(Prefetcher(batches, "cuda")) == 5
     assert list(Prefetcher([], "cuda")) == []
+
+
+def test_warm_started_graph_build_never_changes_the_result():
+    """gdn_graph_build_warm: last build's K-th cosine per row only accelerates the tcgen05 engine.
+    Sequence of small embedding updates (as one Adam step makes), a large jump, and deliberately wrong
+    hints (too high -> flagged and recomputed exactly; too low -> just slower): always bit-identical to
+    the exact fp32 engine, and the returned K-th cosines are the true ones."""
+    from gdn_b200 import ops
+    torch.manual_seed(4)
+    N, D, K = 4096, 128, 32
+    V = (torch.rand(N, D, device="cuda") * 2 - 1) / D ** 0.5
+    kth = torch.full((N,), float("-inf"), device="cuda")
+    for step in range(5):
+        i0, n0 = ops.graph_build(V, K, use_tensor_cores=0)
+        i1, n1 = ops.graph_build(V, K, use_tensor_cores=1, kth=kth, margin=0.03)
+        assert torch.equal(i0, i1) and torch.equal(n0, n1), step
+        Vn = torch.nn.functional.normalize(V.double(), dim=1)
+        want = torch.gather(Vn @ Vn.T, 1, i0)[:, -1]
+        assert (kth.double() - want).abs().max().item() < 1e-5
+        if step == 1:
+            kth[::7] = 0.95                       # absurdly high hints: those rows find < L candidates
+            kth[1::7] = -0.5                      # uselessly low hints
+        scale = 1e-3 if step < 3 else 0.2         # Adam-sized steps, then a jump
+        V = V + scale * torch.sign(torch.randn_like(V)) * V.abs().mean()
