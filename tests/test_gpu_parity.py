@@ -401,3 +401,40 @@ def test_warm_started_graph_build_never_changes_the_result():
             kth[1::7] = -0.5                      # uselessly low hints
         scale = 1e-3 if step < 3 else 0.2         # Adam-sized steps, then a jump
         V = V + scale * torch.sign(torch.randn_like(V)) * V.abs().mean()
+
+
+@pytest.mark.parametrize("shape", [
+    # (N, W, D, K, B): window counts off the 32-lane grid, slide_win 1 / 32, dim 32 / 256, topk 1 / N
+    (40, 1, 32, 1, 3), (33, 32, 256, 33, 33), (70, 7, 64, 69, 65), (130, 16, 128, 64, 1), (64, 12, 64, 9, 96),
+], ids=["W1-K1-B3", "W32-D256-K=N", "K=N-1-B65", "B1", "W12-B96"])
+def test_ragged_shapes_train_step_against_oracle(shape):
+    from gdn_b200.models.GDN import GDN
+    N, W, D, K, B = shape
+    sd = go.init_state(N, D, W, seed=21, stressed=True)
+    g = torch.Generator().manual_seed(5)
+    x, y = torch.rand(B, N, W, generator=g), torch.rand(B, N, generator=g)
+    mask = go.dropout_mask(B, N, D, seed=9)
+    model = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    model.set_dropout_mask(mask.cuda())
+    pred = model(x.cuda(), None)
+    loss = torch.nn.functional.mse_loss(pred, y.cuda())
+    loss.backward()
+    sd64 = go.cast_state(sd, torch.float64)
+    l64, p64, g64, aux = go.loss_and_grads(sd64, x.double(), y.double(), K, drop_mask=mask.double())
+    l32, p32, g32, _ = go.loss_and_grads({k: v.clone() for k, v in sd.items()}, x, y, K, drop_mask=mask)
+    assert torch.equal(model.learned_graph.cpu(), aux["learned_graph"])
+    assert normwise(pred.detach().cpu(), p64) < TOL
+    assert abs(loss.item() - l64.item()) <= TOL * abs(l64.item())
+    for k, p in model.named_parameters():
+        _grad_ok(k, p.grad, g64[k], g32[k])
+    model.eval()
+    with torch.no_grad():
+        pe = model(x.cuda(), None)
+    sd_now = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}   # running stats moved
+    pe_o, aux_e = go.gdn_forward(sd_now, x, K, training=False)
+    assert normwise(pe.cpu(), pe_o) < TOL
+    layer = model.gnn_layers[0]
+    assert torch.equal(layer.edge_index_1.cpu(), aux_e["edge_index"])
+    assert normwise(layer.att_weight_1.cpu(), aux_e["alpha"]) < TOL
