@@ -373,10 +373,17 @@ def run_ours(args):
         fb, bb = graphlayer_bytes(wl)
         f_ms, b_ms = statistics.mean(fwd_ms), statistics.mean(bwd_ms)
         achieved = (fb + bb) / ((f_ms + b_ms) * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[name]["graphlayer_fwd_bwd_dram_bytes"]
+        except Exception:
+            pass
         line["roofline"] = {
             "kernel": "GraphLayer fwd+bwd at the module boundary (gdn_graphlayer_fwd + gdn_graphlayer_bwd)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src, "algorithmic_bytes": fb + bb,
+            "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full: dram__bytes_read.sum + "
+            "dram__bytes_write.sum over the 13 kernels of one fwd+bwd)" if traffic else None,
+            "peak_source": peak_src, "algorithmic_bytes": fb + bb,
             "fwd_ms": f_ms, "bwd_ms": b_ms,
             "fwd_frac": fb / (f_ms * 1e-3) / 1e9 / peak, "bwd_frac": bb / (b_ms * 1e-3) / 1e9 / peak,
             "kernels_ms": {k: round(t / c, 5) for k, (c, t) in sorted(gl_rows.items(), key=lambda kv: -kv[1][1])},

@@ -7,7 +7,10 @@ import sys
 
 rep = sys.argv[1]
 title = sys.argv[2] if len(sys.argv) > 2 else rep
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 idx = {h: i for i, h in enumerate(hdr)}
