@@ -189,7 +189,7 @@ __global__ void k_attn_alpha(const float* __restrict__ siT, const float* __restr
 // is saved by the forward.  One sweep over the edges, no stash, no second exp.
 // ---------------------------------------------------------------------------------------
 template <int WP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_attn_bwd(const float* __restrict__ xT, const float* __restrict__ siT, const float* __restrict__ sjT,
            const float* __restrict__ mT, const float* __restrict__ linvT,
            const int32_t* __restrict__ nbr, const float* __restrict__ gA, const float* __restrict__ A,
