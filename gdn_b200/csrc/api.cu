@@ -135,6 +135,8 @@ CtxLayout ctx_layout(const Shape& s, bool fused) {
     L.bn = take(&off, fused ? (size_t)8 * s.D * sizeof(float) : 0);
     L.bits = take(&off, fused ? (size_t)s.n * s.DPL * sizeof(uint32_t) : 0);
     L.flags = take(&off, 4 * sizeof(int));
+    // last, so that the attention part of the layout is the same with and without it
+    L.xh1 = take(&off, (fused && s.D <= 128) ? (size_t)s.n * s.D * sizeof(float) : 0);
     L.total = off;
     return L;
 }
@@ -149,7 +151,7 @@ WsLayout ws_layout(const Shape& s, bool fused) {
     size_t rec = (size_t)s.D * s.W + s.D;
     if ((size_t)3 * s.D + 32 > rec) rec = (size_t)3 * s.D + 32;
     if ((size_t)s.W * s.W + s.W > rec) rec = (size_t)s.W * s.W + s.W;
-    L.part_bytes = (size_t)2 * num_sms() * rec * sizeof(double);
+    L.part_bytes = (size_t)4 * num_sms() * rec * sizeof(double);
     L.part = take(&off, L.part_bytes);
     L.gV = take(&off, (fused && s.S > 1) ? (size_t)s.S * s.N * s.D * sizeof(float) : 0);
     // small: c2[2D] c1[2D] gev[2N] part_u[2*sms*64] part_e[2*sms*2D]   (floats)
@@ -180,6 +182,9 @@ static HeadArgs head_args(const Shape& s, const char* ctx, const CtxLayout& L, c
     a.V = V;
     a.Wl = p->lin_weight;
     a.bnc = (const float*)(ctx + L.bn);
+    // training passes read the BatchNorm-1 input back instead of recomputing Wl.A (measured: the recompute
+    // passes are FMA-issue bound at 0.30-0.64 ms each at C5; re-reading n*D floats is HBM-bound at ~0.1 ms)
+    a.xh1 = (training && s.D <= 128) ? (float*)(const_cast<char*>(ctx) + L.xh1) : nullptr;
     a.g1 = h->bn1.weight; a.be1 = h->bn1.bias; a.g2 = h->bn2.weight; a.be2 = h->bn2.bias;
     a.wo = h->out_w; a.bo = h->out_b;
     a.B = s.B; a.N = s.N; a.W = s.W; a.D = s.D; a.S = s.S; a.rps = s.rows_per_split;

@@ -73,6 +73,7 @@ struct CtxLayout {
     size_t ev;      // e_i[N], e_j[N]
     size_t bn;      // mean1[D], istd1[D], mean2[D], istd2[D]     (fused path)
     size_t bits;    // [n][D/32] uint32 dropout keep bits          (fused path)
+    size_t xh1;     // [n][D] saved BatchNorm-1 input xh1 (fused training path, D <= 128)
     size_t flags;   // int[4]: training, ...
     size_t total;
 };

@@ -173,6 +173,37 @@ struct RowStage {
     }
 };
 
+// Per-lane prefetch buffer for the saved BatchNorm-1 input xh1[r, :] (training path): lane l copies
+// its own DPL channels of up to 32 rows into shared memory with cp.async (all copies in flight at once,
+// no registers held), then reads them back itself -- no cross-lane traffic, no barrier beyond the wait.
+constexpr int XH_ROWS = 16;      // rows per batch of the buffered passes (8 KB per warp at D = 128: 3 CTAs per SM)
+template <int DPL>
+struct XhStage {
+    static constexpr int WARP_FLOATS = XH_ROWS * DPL * 32;
+    __device__ __forceinline__ static void fill(float* sx, const float* __restrict__ first, size_t row_stride,
+                                                int nb, int lane) {
+        for (int rr = 0; rr < nb; ++rr) {
+            const float* src = first + (size_t)rr * row_stride + lane * DPL;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sx + (rr * 32 + lane) * DPL);
+            if (DPL == 4) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            } else if (DPL == 8) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"(src + 4) : "memory");
+            } else if (DPL == 2) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+            } else {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ static void wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+    __device__ __forceinline__ static void get(const float* sx, int rr, int lane, float (&v)[DPL]) {
+        load_chan_vec<DPL>(sx + rr * 32 * DPL, lane, v);
+    }
+};
+
 // ---------------------------------------------------------------------------------------
 // module boundary: out[r,:] = Wl.A[r,:] + bias            (models/graph_layer.py:56,71-74)
 // ---------------------------------------------------------------------------------------
@@ -410,8 +441,8 @@ template <int DPL, int WP>
 struct RowEval {
     float wl[DPL][WP];
     float k1a[DPL], k1b[DPL], g1[DPL], be1[DPL];
-    __device__ __forceinline__ void init(const HeadArgs& h, int lane) {
-        load_wl<DPL, WP>(h.Wl, h.W, lane, wl);
+    __device__ __forceinline__ void init(const HeadArgs& h, int lane, bool need_wl = true) {
+        if (need_wl) load_wl<DPL, WP>(h.Wl, h.W, lane, wl);
         load_chan<DPL>(h.bnc + 2 * h.D, lane, k1a);
         load_chan<DPL>(h.bnc + 3 * h.D, lane, k1b);
         load_chan<DPL>(h.g1, lane, g1);
@@ -428,7 +459,26 @@ struct RowEval {
             y1[j] = fmaf(g1[j], xh1[j], be1[j]);
         }
     }
+    // same, xh1 taken from the buffer the forward saved
+    __device__ __forceinline__ void from_saved(const float (&xh1)[DPL], float (&y1)[DPL]) const {
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) y1[j] = fmaf(g1[j], xh1[j], be1[j]);
+    }
 };
+
+// inputs of one row for the D-wide passes: A row (if the pass needs it) and (xh1, y1), either
+// recomputed from A or read back from the saved buffer
+template <int DPL, int WP, bool NEED_A, bool BUF>
+__device__ __forceinline__ void row_inputs(const RowEval<DPL, WP>& re, const float* sa, const float* sx, int rr, int lane,
+                                           float (&a)[WP], float (&xh1)[DPL], float (&y1)[DPL]) {
+    if (NEED_A) RowStage<WP>::get(sa, rr, a);
+    if (BUF) {
+        XhStage<DPL>::get(sx, rr, lane, xh1);
+        re.from_saved(xh1, y1);
+    } else {
+        re.eval(a, xh1, y1);
+    }
+}
 
 #define GDN_TASK_LOOP_BEGIN(h)                                                                   \
     const int lane = threadIdx.x & 31;                                                           \
@@ -436,22 +486,30 @@ struct RowEval {
     const long long nwarps_ = ((long long)gridDim.x * blockDim.x) >> 5;                          \
     const long long tasks_ = (long long)(h).N * (h).S;                                           \
     const size_t rstride_ = (size_t)(h).N * (h).W;                                               \
-    float* sa_ = RowStage<WP>::tile();                                                           \
+    constexpr int WARP_SMEM_ = (NEED_A_ ? RowStage<WP>::WARP_FLOATS : 0) + (BUF_ ? XhStage<DPL>::WARP_FLOATS : 0); \
+    float* sa_ = reinterpret_cast<float*>(dyn_smem) + (size_t)(threadIdx.x >> 5) * WARP_SMEM_;   \
+    float* sx_ = sa_ + (NEED_A_ ? RowStage<WP>::WARP_FLOATS : 0);                                \
     for (long long task_ = warp_; task_ < tasks_; task_ += nwarps_) {                            \
         const int i = (int)(task_ / (h).S), sp = (int)(task_ % (h).S);                           \
         const int b_lo = sp * (h).rps, b_hi = min((h).B, b_lo + (h).rps);
 #define GDN_TASK_LOOP_END }
 // inside a task: batches of up to 32 windows of sensor i
 #define GDN_BATCH_LOOP_BEGIN(h)                                                                  \
-    for (int b0 = b_lo; b0 < b_hi; b0 += 32) {                                                   \
-        const int nb = min(32, b_hi - b0);                                                       \
-        RowStage<WP>::fill(sa_, (h).A + ((size_t)b0 * (h).N + i) * (h).W, rstride_, nb, (h).W, lane);
+    for (int b0 = b_lo; b0 < b_hi; b0 += (BUF_ ? XH_ROWS : 32)) {                                \
+        const int nb = min(BUF_ ? XH_ROWS : 32, b_hi - b0);                                      \
+        if (BUF_) {                                                                              \
+            __syncwarp();                                                                        \
+            XhStage<DPL>::fill(sx_, (h).xh1 + ((size_t)b0 * (h).N + i) * (h).D, (size_t)(h).N * (h).D, nb, lane); \
+        }                                                                                        \
+        if (NEED_A_) RowStage<WP>::fill(sa_, (h).A + ((size_t)b0 * (h).N + i) * (h).W, rstride_, nb, (h).W, lane); \
+        if (BUF_) XhStage<DPL>::wait();
 #define GDN_BATCH_LOOP_END }
 
 // BN2 batch statistics: sum_r p, sum_r p^2 -> part record [2*D] doubles
 template <int DPL, int WP>
 __global__ void __launch_bounds__(256)
 k_fwd_stats2(HeadArgs h, double* __restrict__ part) {
+    constexpr bool NEED_A_ = true, BUF_ = false;
     RowEval<DPL, WP> re;
     re.init(h, threadIdx.x & 31);
     double acc[2 * DPL];
@@ -466,8 +524,8 @@ k_fwd_stats2(HeadArgs h, double* __restrict__ part) {
 #pragma unroll 2
             for (int rr = 0; rr < nb; ++rr) {
                 float a[WP], xh1[DPL], y1[DPL];
-                RowStage<WP>::get(sa_, rr, a);
-                re.eval(a, xh1, y1);
+                row_inputs<DPL, WP, NEED_A_, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
+                if (h.xh1 != nullptr) store_chan<DPL>(h.xh1 + ((size_t)(b0 + rr) * h.N + i) * h.D, lane, xh1);
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) {
                     const float p = fmaxf(y1[j], 0.f) * v[j];
@@ -519,11 +577,12 @@ __device__ __forceinline__ void gen_keep_words(const HeadArgs& h, size_t r, uint
 }
 
 // pred[b,i] = sum_d hm[d] wo[d] + bo;  training: dropout + keep bits saved
-template <int DPL, int WP>
+template <int DPL, int WP, bool BUF_>
 __global__ void __launch_bounds__(256)
 k_fwd_out(HeadArgs h, float* __restrict__ pred) {
+    constexpr bool NEED_A_ = !BUF_;
     RowEval<DPL, WP> re;
-    re.init(h, threadIdx.x & 31);
+    re.init(h, threadIdx.x & 31, NEED_A_);
     float k2a[DPL], k2b[DPL], g2[DPL], be2[DPL], wo[DPL];
     {
         const int ln = threadIdx.x & 31;
@@ -547,8 +606,7 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
 #pragma unroll 2
             for (int rr = 0; rr < nb; ++rr) {
                 float a[WP], xh1[DPL], y1[DPL];
-                RowStage<WP>::get(sa_, rr, a);
-                re.eval(a, xh1, y1);
+                row_inputs<DPL, WP, NEED_A_, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
                 float dot = 0.f;
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) {
@@ -619,12 +677,13 @@ struct BwdSide {
 };
 
 // pass 1: g_wo, g_gamma2, g_beta2, g_bo   -> part record [3*D + 32] doubles
-template <int DPL, int WP>
+template <int DPL, int WP, bool BUF_>
 __global__ void __launch_bounds__(256)
 k_bwd1(HeadArgs h, BwdArgs g, double* __restrict__ part) {
+    constexpr bool NEED_A_ = !BUF_;
     RowEval<DPL, WP> re;
     BwdRow<DPL, WP> br;
-    re.init(h, threadIdx.x & 31);
+    re.init(h, threadIdx.x & 31, NEED_A_);
     br.init(h, threadIdx.x & 31);
     double acc[3 * DPL];
 #pragma unroll
@@ -642,8 +701,7 @@ k_bwd1(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 #pragma unroll 2
             for (int rr = 0; rr < nb; ++rr) {
                 float a[WP], xh1[DPL], y1[DPL], kf[DPL];
-                RowStage<WP>::get(sa_, rr, a);
-                re.eval(a, xh1, y1);
+                row_inputs<DPL, WP, NEED_A_, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
                 const float gp = side.row(h, rr, lane, kf);
                 tb += gp;
 #pragma unroll
@@ -680,12 +738,13 @@ k_bwd1(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 }
 
 // pass 2: g_V (sum over windows), g_gamma1, g_beta1     -> part record [2*D] doubles
-template <int DPL, int WP>
+template <int DPL, int WP, bool BUF_>
 __global__ void __launch_bounds__(256)
 k_bwd2(HeadArgs h, BwdArgs g, double* __restrict__ part) {
+    constexpr bool NEED_A_ = !BUF_;
     RowEval<DPL, WP> re;
     BwdRow<DPL, WP> br;
-    re.init(h, threadIdx.x & 31);
+    re.init(h, threadIdx.x & 31, NEED_A_);
     br.init(h, threadIdx.x & 31);
     float cB2[DPL], cG2[DPL], s2c[DPL];
     {
@@ -709,8 +768,7 @@ k_bwd2(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 #pragma unroll 2
             for (int rr = 0; rr < nb; ++rr) {
                 float a[WP], xh1[DPL], y1[DPL], kf[DPL];
-                RowStage<WP>::get(sa_, rr, a);
-                re.eval(a, xh1, y1);
+                row_inputs<DPL, WP, NEED_A_, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
                 const float gp = side.row(h, rr, lane, kf);
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) {
@@ -737,9 +795,10 @@ k_bwd2(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 
 // pass 3: g_A[r,:] = g_z.Wl, partial g_Wl += g_z (x) A, partial g_bias += g_z
 // part record: [D*W + D] doubles
-template <int DPL, int WP>
+template <int DPL, int WP, bool BUF_>
 __global__ void __launch_bounds__(256)
 k_bwd3(HeadArgs h, BwdArgs g, double* __restrict__ part) {
+    constexpr bool NEED_A_ = true;
     RowEval<DPL, WP> re;
     BwdRow<DPL, WP> br;
     re.init(h, threadIdx.x & 31);
@@ -771,8 +830,7 @@ k_bwd3(HeadArgs h, BwdArgs g, double* __restrict__ part) {
             for (int rr = 0; rr < nb; ++rr) {
                 const size_t r = (size_t)(b0 + rr) * h.N + i;
                 float a[WP], xh1[DPL], y1[DPL], kf[DPL], pw[WP];
-                RowStage<WP>::get(sa_, rr, a);
-                re.eval(a, xh1, y1);
+                row_inputs<DPL, WP, NEED_A_, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
                 const float gp = side.row(h, rr, lane, kf);
 #pragma unroll
                 for (int w = 0; w < WP; ++w) pw[w] = 0.f;
@@ -1050,6 +1108,16 @@ static size_t dw_smem(int nv_double, bool red33) {
     if (r2 > b) b = r2;
     return b;
 }
+// per-warp staging of the fused passes: A tile (if needed) + saved-xh1 tile (if buffered)
+template <int DPL, int WP>
+static size_t dw_smem2(bool need_a, bool buf, int nv_double, bool red33) {
+    size_t b = (size_t)8 * ((need_a ? RowStage<WP>::WARP_FLOATS : 0) + (buf ? XhStage<DPL>::WARP_FLOATS : 0)) * sizeof(float);
+    const size_t r1 = (size_t)8 * nv_double * 32 * sizeof(double);
+    const size_t r2 = red33 ? (size_t)8 * 33 * 32 * sizeof(float) : 0;
+    if (r1 > b) b = r1;
+    if (r2 > b) b = r2;
+    return b;
+}
 #define GDN_LAUNCH_DYN(KERNEL, GRID, SMEM, ST, ...)                                                     \
     do {                                                                                               \
         const size_t sm__ = (SMEM);                                                                    \
@@ -1062,7 +1130,7 @@ static size_t dw_smem(int nv_double, bool red33) {
 
 static int dw_grid(long long tasks) {
     long long g = (tasks + 7) / 8;
-    const int cap = 2 * num_sms();
+    const int cap = 4 * num_sms();      // ws partial-record regions are sized for this many CTAs
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -1137,7 +1205,7 @@ int launch_fin_bn_eval(const Shape& s, const gdn_layer_params* p, const gdn_head
 int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, double* sums, const gdn_bn* bn, float* bnc,
                       cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_fwd_stats2<DPLC, WPC>), grid, dw_smem<WPC>(2 * DPLC, false), st, h, part)
+#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_fwd_stats2<DPLC, WPC>), grid, (dw_smem2<DPLC, WPC>(true, false, 2 * DPLC, false)), st, h, part)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_fwd_stats2");
@@ -1150,7 +1218,12 @@ int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, double* s
 
 int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_fwd_out<DPLC, WPC>), grid, dw_smem<WPC>(0, false), st, h, pred)
+    const bool buf = h.xh1 != nullptr;
+#define CALL(DPLC, WPC)                                                                                             \
+    do {                                                                                                            \
+        if (buf) GDN_LAUNCH_DYN((k_fwd_out<DPLC, WPC, true>), grid, (dw_smem2<DPLC, WPC>(false, true, 0, false)), st, h, pred); \
+        else GDN_LAUNCH_DYN((k_fwd_out<DPLC, WPC, false>), grid, (dw_smem2<DPLC, WPC>(true, false, 0, false)), st, h, pred);    \
+    } while (0)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_fwd_out");
@@ -1160,7 +1233,12 @@ int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t 
 int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
                 float* c2, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_bwd1<DPLC, WPC>), grid, dw_smem<WPC>(3 * DPLC, false), st, h, g, part)
+    const bool buf = h.xh1 != nullptr;
+#define CALL(DPLC, WPC)                                                                                             \
+    do {                                                                                                            \
+        if (buf) GDN_LAUNCH_DYN((k_bwd1<DPLC, WPC, true>), grid, (dw_smem2<DPLC, WPC>(false, true, 3 * DPLC, false)), st, h, g, part); \
+        else GDN_LAUNCH_DYN((k_bwd1<DPLC, WPC, false>), grid, (dw_smem2<DPLC, WPC>(true, false, 3 * DPLC, false)), st, h, g, part);    \
+    } while (0)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd1");
@@ -1173,7 +1251,12 @@ int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
 int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
                 float* c1, float* gV_final, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_bwd2<DPLC, WPC>), grid, dw_smem<WPC>(2 * DPLC, false), st, h, g, part)
+    const bool buf = h.xh1 != nullptr;
+#define CALL(DPLC, WPC)                                                                                             \
+    do {                                                                                                            \
+        if (buf) GDN_LAUNCH_DYN((k_bwd2<DPLC, WPC, true>), grid, (dw_smem2<DPLC, WPC>(false, true, 2 * DPLC, false)), st, h, g, part); \
+        else GDN_LAUNCH_DYN((k_bwd2<DPLC, WPC, false>), grid, (dw_smem2<DPLC, WPC>(true, false, 2 * DPLC, false)), st, h, g, part);    \
+    } while (0)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd2");
@@ -1192,7 +1275,12 @@ int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
 
 int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
-#define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_bwd3<DPLC, WPC>), grid, dw_smem<WPC>(0, true), st, h, g, part)
+    const bool buf = h.xh1 != nullptr;
+#define CALL(DPLC, WPC)                                                                                             \
+    do {                                                                                                            \
+        if (buf) GDN_LAUNCH_DYN((k_bwd3<DPLC, WPC, true>), grid, (dw_smem2<DPLC, WPC>(true, true, 0, true)), st, h, g, part); \
+        else GDN_LAUNCH_DYN((k_bwd3<DPLC, WPC, false>), grid, (dw_smem2<DPLC, WPC>(true, false, 0, true)), st, h, g, part);   \
+    } while (0)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd3");

@@ -10,6 +10,7 @@ struct HeadArgs {
     const float* V;
     const float* Wl;
     const float* bnc;
+    float* xh1;          // [n][D] saved BatchNorm-1 input (training, D <= 128) or NULL: recompute from A
     const float* g1; const float* be1; const float* g2; const float* be2;
     const float* wo; const float* bo;
     int B, N, W, D, S, rps;
