@@ -369,13 +369,15 @@ k_lin_bwd(const float* __restrict__ gout, const float* __restrict__ A, const flo
 template <int WP>
 __global__ void __launch_bounds__(256)
 k_moments(const float* __restrict__ A, long long n, int W, double* __restrict__ part) {
-    constexpr int NW = WP == 32 ? 4 : 8;        // warps per CTA (static smem stays < 48 KB)
+    constexpr int NW = WP == 32 ? 2 : 8;        // warps per CTA (static smem stays < 48 KB)
     __shared__ double red[NW][WP + 1][WP];
+    __shared__ __align__(16) float stage[NW][RowStage<WP>::WARP_FLOATS];
     constexpr int SLOTS = 32 / WP;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int slot = lane / WP, wq = lane % WP;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    float* sa = stage[wid];
     float acc[WP];
 #pragma unroll
     for (int w = 0; w < WP; ++w) acc[w] = 0.f;
@@ -383,23 +385,22 @@ k_moments(const float* __restrict__ A, long long n, int W, double* __restrict__ 
     double dacc[WP], ds1 = 0.0;
 #pragma unroll
     for (int w = 0; w < WP; ++w) dacc[w] = 0.0;
-    int since = 0;
-    for (long long r0 = warp * SLOTS; r0 < n; r0 += nwarps * SLOTS) {
-        const long long r = r0 + slot;
-        if (r < n) {
+    // 32 rows per batch staged in shared memory (one coalesced burst), then lane (slot, w') walks the
+    // rows of its slot: fp32 partials are flushed into fp64 after every batch
+    for (long long r0 = warp * 32; r0 < n; r0 += nwarps * 32) {
+        const int nb = (int)((n - r0) < 32 ? (n - r0) : 32);
+        RowStage<WP>::fill(sa, A + (size_t)r0 * W, (size_t)W, nb, W, lane);
+        for (int rr = slot; rr < nb; rr += SLOTS) {
             float a[WP];
-            load_arow<WP>(A + (size_t)r * W, W, a);
-            const float own = (wq < W) ? A[(size_t)r * W + wq] : 0.f;
+            RowStage<WP>::get(sa, rr, a);
+            const float own = sa[rr * RowStage<WP>::STRIDE + wq];
             s1 += own;
 #pragma unroll
             for (int w = 0; w < WP; ++w) acc[w] = fmaf(a[w], own, acc[w]);
         }
-        if (++since == 32) {      // flush fp32 partials into fp64 every 32 rows
-            since = 0;
 #pragma unroll
-            for (int w = 0; w < WP; ++w) { dacc[w] += (double)acc[w]; acc[w] = 0.f; }
-            ds1 += (double)s1; s1 = 0.f;
-        }
+        for (int w = 0; w < WP; ++w) { dacc[w] += (double)acc[w]; acc[w] = 0.f; }
+        ds1 += (double)s1; s1 = 0.f;
     }
 #pragma unroll
     for (int w = 0; w < WP; ++w) dacc[w] += (double)acc[w];
@@ -1174,10 +1175,13 @@ int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_
 }
 
 int launch_moments(const Shape& s, const float* A, double* part, int* nrec, cudaStream_t st) {
-    const int grid = dw_grid((s.n + 3) / 4);
+    const int nw = s.WP == 32 ? 2 : 8;
+    long long g = (s.n + 32LL * nw - 1) / (32LL * nw);
+    if (g > 4 * num_sms()) g = 4 * num_sms();
+    const int grid = (int)(g < 1 ? 1 : g);
     if (s.WP == 8) k_moments<8><<<grid, 256, 0, st>>>(A, s.n, s.W, part);
     else if (s.WP == 16) k_moments<16><<<grid, 256, 0, st>>>(A, s.n, s.W, part);
-    else k_moments<32><<<grid, 128, 0, st>>>(A, s.n, s.W, part);
+    else k_moments<32><<<grid, 64, 0, st>>>(A, s.n, s.W, part);
     GDN_CHECK_LAUNCH("k_moments");
     *nrec = grid;
     return 0;

@@ -394,44 +394,72 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------
 // 3. exact re-score + ranking of the candidates (one warp per row)
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int D, int K, int L, int C,
+constexpr int RS_WARPS = 4;
+template <int D>
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int K, int L, int C,
           const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ rowcnt,
           float* __restrict__ kth_out,
           int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, int* __restrict__ block_flags) {
-    __shared__ float s_cos[8][TC_MAXL];
-    __shared__ int s_j[8][TC_MAXL];
-    __shared__ int s_out[8][TC_MAXL];
+    __shared__ float s_cos[RS_WARPS][TC_MAXL];
+    __shared__ int s_j[RS_WARPS][TC_MAXL];
+    __shared__ int s_out[RS_WARPS][TC_MAXL];
+    extern __shared__ __align__(16) float rs_smem[];        // per warp: candidate tile [32][D+4] + v_i [D]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int i = blockIdx.x * 8 + wid;
+    const int i = blockIdx.x * RS_WARPS + wid;
     if (i >= N) return;
-    const float* vi = V + (size_t)i * D;
+    constexpr int TS = D + 4;                                    // tile row stride: conflict-free float4 row reads
+    float* tile = rs_smem + (size_t)wid * (32 * TS + D);
+    float* svi = tile + 32 * TS;
+    for (int d = 4 * lane; d < D; d += 128)
+        *reinterpret_cast<float4*>(svi + d) = __ldg(reinterpret_cast<const float4*>(V + (size_t)i * D + d));
     const float ni = nrm[i];
     const int have = rowcnt[i];
     for (int k = lane; k < K; k += 32) s_out[wid][k] = i;     // placeholder if the row is short (it is flagged)
     __syncwarp();
     float amin = INFINITY;
-    for (int l = lane; l < L; l += 32) {
-        const int j = l < have ? cand_idx[(size_t)i * C + l] : -1;
-        float c = -INFINITY;
-        if (j >= 0) {
-            // one fmaf chain over d = 0..D-1, exactly as graph_build.cu accumulates it; 16-byte loads
-            const float4* vi4 = reinterpret_cast<const float4*>(vi);
-            const float4* vj4 = reinterpret_cast<const float4*>(V + (size_t)j * D);
-            float dot = 0.f;
-#pragma unroll 8
-            for (int q = 0; q < D / 4; ++q) {
-                const float4 a = __ldg(vi4 + q), b = __ldg(vj4 + q);
-                dot = fmaf(a.x, b.x, dot);
-                dot = fmaf(a.y, b.y, dot);
-                dot = fmaf(a.z, b.z, dot);
-                dot = fmaf(a.w, b.w, dot);
+    for (int l0 = 0; l0 < L; l0 += 32) {
+        const int l = l0 + lane;
+        const int j = (l < L && l < have) ? cand_idx[(size_t)i * C + l] : -1;
+        // stage the 32 candidate rows with coalesced 16-byte loads, 8 loads in flight per lane
+        constexpr int LPR = D / 4, RPP = 32 / LPR;            // lanes per row, rows per warp-wide load
+        const int sub = lane / LPR, dq = 4 * (lane % LPR);
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8 * RPP) {
+            float4 r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int jc = __shfl_sync(0xffffffffu, j, c0 + u * RPP + sub);
+                r[u] = jc >= 0 ? __ldg(reinterpret_cast<const float4*>(V + (size_t)jc * D + dq))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            c = dot / (ni * nrm[j]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                *reinterpret_cast<float4*>(tile + (c0 + u * RPP + sub) * TS + dq) = r[u];
         }
-        s_cos[wid][l] = c;
-        s_j[wid][l] = j;
-        amin = fminf(amin, l < have ? cand_val[(size_t)i * C + l] : -INFINITY);
+        __syncwarp();
+        if (l < L) {
+            float c = -INFINITY;
+            if (j >= 0) {
+                // one fmaf chain over d = 0..D-1, exactly as graph_build.cu accumulates it
+                const float4* vj4 = reinterpret_cast<const float4*>(tile + lane * TS);
+                const float4* vi4 = reinterpret_cast<const float4*>(svi);
+                float dot = 0.f;
+#pragma unroll 8
+                for (int q = 0; q < D / 4; ++q) {
+                    const float4 a = vi4[q], b = vj4[q];
+                    dot = fmaf(a.x, b.x, dot);
+                    dot = fmaf(a.y, b.y, dot);
+                    dot = fmaf(a.z, b.z, dot);
+                    dot = fmaf(a.w, b.w, dot);
+                }
+                c = dot / (ni * nrm[j]);
+            }
+            s_cos[wid][l] = c;
+            s_j[wid][l] = j;
+            amin = fminf(amin, l < have ? cand_val[(size_t)i * C + l] : -INFINITY);
+        }
+        __syncwarp();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o));
@@ -448,7 +476,7 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int
         for (int q = 0; q < L; ++q) {
             const float cq = s_cos[wid][q];
             const int jq = s_j[wid][q];
-            rank += (cq > c || (cq == c && jq < j)) ? 1 : 0;
+            rank += (int)(cq > c) | ((int)(cq == c) & (int)(jq < j));
         }
         if (j >= 0 && rank < K) s_out[wid][rank] = j;
         if (j >= 0 && rank == K - 1 && kth_out != nullptr) kth_out[i] = c;
@@ -544,7 +572,12 @@ int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* n
     k_gram_tc<<<ceil_div(N, TC_BM), 256, smem, st>>>(tm_hi, tm_lo, N, KB, L, C, bufv, bufj, rowcnt, kth, margin, flags,
                                                      err, dbg);
     GDN_CHECK_LAUNCH("k_gram_tc");
-    k_rescore<<<ceil_div(N, 8), 256, 0, st>>>(V, nrm, N, D, K, L, C, bufv, bufj, rowcnt, kth, idx, nbr, flags);
+    const size_t rs_smem = (size_t)RS_WARPS * (32 * (D + 4) + D) * sizeof(float);
+    auto rescore = D == 128 ? k_rescore<128> : k_rescore<64>;
+    e = ensure_dyn_smem_ptr(reinterpret_cast<const void*>(rescore), rs_smem);
+    if (e != cudaSuccess) return cuda_fail(e, "smem attr k_rescore");
+    rescore<<<ceil_div(N, RS_WARPS), RS_WARPS * 32, rs_smem, st>>>(V, nrm, N, K, L, C, bufv, bufj, rowcnt, kth, idx, nbr,
+                                                                  flags);
     GDN_CHECK_LAUNCH("k_rescore");
     *nrm_out = nrm;
     *flags_out = flags;
