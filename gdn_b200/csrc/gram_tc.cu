@@ -29,9 +29,11 @@
 namespace gdn {
 
 constexpr int TC_BM = 128;        // rows per CTA = UMMA M
-constexpr int TC_BN = 64;         // columns per tile = UMMA N
+constexpr int TC_BN = 128;        // columns per tile = UMMA N (N < 128 leaves the MMA bound by its A-operand reads)
 constexpr int TC_BK = 64;         // bf16 per k-block: 128 bytes = one SWIZZLE_128B atom row
 constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 384;
+constexpr int TC_MAXSPLIT = 4;     // column splits per row block (x 2 warpgroups = candidate segments per row)
 constexpr int TC_SLACK = 8;
 constexpr int TC_MAXL = 80;
 constexpr int TC_MAXC = 256;      // buffer capacity (8 entries per lane in a compaction)
@@ -105,6 +107,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for the outstanding tcgen05.ld; the registers are in/out operands so that no use of them can be
+// scheduled above the wait when the load was issued earlier (software pipelining)
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4,
 // LBO = 0 (a single swizzle atom along K), SBO = 1024 bytes (8 rows x 128 bytes), version 1.
@@ -115,7 +125,7 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// instruction descriptor: D = F32, A = B = BF16, both K-major, N = 64, M = 128
+// instruction descriptor: D = F32, A = B = BF16, both K-major, N = TC_BN, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                               ((uint32_t)(TC_BM >> 4) << 24);
 
@@ -149,21 +159,24 @@ __global__ void k_normalise_split(const float* __restrict__ V, int N, int D, flo
 // ---------------------------------------------------------------------------------------
 // 2. tcgen05 Gram + per-row candidate selection
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+// grid (row blocks, column splits); 12 warps: 0 = TMA, 1 = MMA, 2 = TMEM alloc, 4-7 / 8-11 = the two
+// epilogue warpgroups.  Warpgroup g consumes the tiles whose accumulator lives in TMEM buffer g (every
+// other tile), so the two filter streams overlap; each (column split, warpgroup) pair owns its own
+// candidate segment of every row: segment = 2 * blockIdx.y + g, merged by k_rescore.
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-          int N, int KB, int L, int C, float* __restrict__ bufv, int* __restrict__ bufj, int* __restrict__ rowcnt,
-          const float* __restrict__ hint, float margin, int* __restrict__ flags, int* __restrict__ err, int dbg) {
+          int N, int KB, int L, int C, int tiles_per_split, float* __restrict__ bufv, int* __restrict__ bufj,
+          int* __restrict__ rowcnt, const float* __restrict__ hint, float margin, int* __restrict__ err, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B atoms: 1024-byte aligned
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t A_BYTES = (uint32_t)KB * TC_BM * 128;                 // one of hi / lo
-    const uint32_t B_BYTES = (uint32_t)KB * TC_BN * 128;                 // one of hi / lo, one stage
+    constexpr uint32_t B_BYTES = TC_BN * 128;                            // one of hi / lo, one k-block = half a stage
     const uint32_t sA = base;                                            // [2][KB][128 x 128 B]
-    const uint32_t sB = sA + 2 * A_BYTES;                                // [STAGES][2][KB][64 x 128 B]
+    const uint32_t sB = sA + 2 * A_BYTES;                                // [STAGES][2][TC_BN x 128 B]; stage <-> (tile, kb)
     const uint32_t off_stage = 2 * A_BYTES + TC_STAGES * 2 * B_BYTES;
-    float* p_vals = reinterpret_cast<float*>(gbase + off_stage);         // [17][128] filter staging (slot 16 = trash)
-    int* p_idxs = reinterpret_cast<int*>(p_vals + 17 * TC_BM);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p_idxs + 17 * TC_BM);
+    float* p_vals = reinterpret_cast<float*>(gbase + off_stage);         // [2][16][128] filter staging per warpgroup
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_vals + 2 * 16 * TC_BM);
     const uint32_t bar0 = smem_u32(bars);
     const uint32_t b_afull = bar0, b_full = bar0 + 8, b_empty = b_full + 8 * TC_STAGES,
                    b_tfull = b_empty + 8 * TC_STAGES, b_tempty = b_tfull + 16;
@@ -171,7 +184,9 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM;
-    const int ntiles = (N + TC_BN - 1) / TC_BN;
+    const int S = 2 * (int)gridDim.y;                                    // candidate segments per row
+    const int tile0 = blockIdx.y * tiles_per_split;                      // this CTA sweeps tiles [tile0, tile0 + ntiles)
+    const int ntiles = min(tiles_per_split, (N + TC_BN - 1) / TC_BN - tile0);
 
     if (threadIdx.x == 0) {
         mbar_init(b_afull, 1);
@@ -197,32 +212,37 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
                 for (int half = 0; half < 2; ++half)
                     tma_load_2d(sA + h * A_BYTES + kb * (TC_BM * 128) + half * (64 * 128), h ? &tm_lo : &tm_hi, b_afull,
                                 kb * TC_BK, m0 + half * 64);
-        for (int t = 0; t < ntiles; ++t) {
-            const int s = t % TC_STAGES;
-            const uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u;
+        for (int it = 0; it < ntiles * KB; ++it) {
+            const int t = it / KB, kb = it - t * KB;
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
             if (!mbar_wait(b_empty + 8 * s, ph ^ 1u, err, 1)) break;
             mbar_expect_tx(b_full + 8 * s, 2 * B_BYTES);
             for (int h = 0; h < 2; ++h)
-                for (int kb = 0; kb < KB; ++kb)
-                    tma_load_2d(sB + (s * 2 + h) * B_BYTES + kb * (TC_BN * 128), h ? &tm_lo : &tm_hi, b_full + 8 * s,
-                                kb * TC_BK, t * TC_BN);
+                for (int half = 0; half < TC_BN / 64; ++half)
+                    tma_load_2d(sB + (s * 2 + h) * B_BYTES + half * (64 * 128), h ? &tm_lo : &tm_hi, b_full + 8 * s,
+                                kb * TC_BK, (tile0 + t) * TC_BN + half * 64);
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer (one thread) =====
         bool ok = mbar_wait(b_afull, 0, err, 2);
         for (int t = 0; ok && t < ntiles; ++t) {
-            const int s = t % TC_STAGES, acc = t & 1;
-            const uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u, aph = (uint32_t)(t >> 1) & 1u;
+            const int acc = t & 1;
+            const uint32_t aph = (uint32_t)(t >> 1) & 1u;
             if (!mbar_wait(b_tempty + 8 * acc, aph ^ 1u, err, 3)) break;
-            if (!mbar_wait(b_full + 8 * s, ph, err, 4)) break;
-            tc_fence_after();
             uint32_t accumulate = 0;
+            for (int kb = 0; kb < KB; ++kb) {
+                const int it = t * KB + kb;
+                const int s = it % TC_STAGES;
+                const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                if (!mbar_wait(b_full + 8 * s, ph, err, 4)) { ok = false; break; }
+                tc_fence_after();
 #pragma unroll
-            for (int prod = 0; prod < 3; ++prod) {                      // hi.hi, hi.lo, lo.hi
-                const int ah = prod == 2 ? 1 : 0, bh = prod == 1 ? 1 : 0;
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int prod = 0; prod < 3; ++prod) {                  // hi.hi, hi.lo, lo.hi
+                    if ((dbg & 2) && prod > 0) break;
+                    const int ah = prod == 2 ? 1 : 0, bh = prod == 1 ? 1 : 0;
                     const uint32_t a0 = sA + ah * A_BYTES + kb * (TC_BM * 128);
-                    const uint32_t b0 = sB + (s * 2 + bh) * B_BYTES + kb * (TC_BN * 128);
+                    const uint32_t b0 = sB + (s * 2 + bh) * B_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
                         tc_mma_f16(tmem_base + acc * TC_BN, sw128_desc(a0 + k * 32), sw128_desc(b0 + k * 32), TC_IDESC,
@@ -230,8 +250,9 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
                         accumulate = 1;
                     }
                 }
+                tc_commit(b_empty + 8 * s);      // smem stage reusable once these MMAs have read it
             }
-            tc_commit(b_empty + 8 * s);          // smem stage reusable once these MMAs have read it
+            if (!ok) break;
             tc_commit(b_tfull + 8 * acc);        // accumulator ready for the epilogue
         }
     } else if (warp >= 4) {
@@ -244,12 +265,13 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
         //     rank, and raise the threshold to the L-th value.  The threshold is only refreshed at
         //     compactions, so a row is compacted ~1 + ln(N / 2L) times per sweep instead of paying a
         //     minimum search per admitted element.
-        const int wrow0 = (warp - 4) * 32;           // first row of this warp inside the CTA
+        const int wg = (warp - 4) >> 2;              // epilogue warpgroup = TMEM accumulator buffer it drains
+        const int seg = 2 * (int)blockIdx.y + wg;    // candidate segment of this (column split, warpgroup)
+        const int wrow0 = (warp & 3) * 32;           // first row of this warp inside the CTA (= its TMEM lanes)
         const int row = wrow0 + lane;
-        float* bv = bufv + (size_t)(m0 + row) * C;
-        int* bj = bufj + (size_t)(m0 + row) * C;
-        float* pv = p_vals + row;                    // staging slot q of row r at [q * 128 + r]; slot 16 = trash
-        int* pj = p_idxs + row;
+        float* bv = bufv + ((size_t)(m0 + row) * S + seg) * C;
+        int* bj = bufj + ((size_t)(m0 + row) * S + seg) * C;
+        float* pv = p_vals + wg * 16 * TC_BM + row;  // staging slot q of row r at [q * 128 + r]
         int cnt = 0;
         // Warm start: the caller may pass last step's K-th cosine per row.  The embedding moves by one
         // optimiser step between graph builds, so (hint - margin) is a valid admission threshold for
@@ -277,8 +299,8 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
                 const int rr = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int cnt_r = __shfl_sync(0xffffffffu, cnt, rr);
-                float* gv = bufv + (size_t)(m0 + wrow0 + rr) * C;
-                int* gj = bufj + (size_t)(m0 + wrow0 + rr) * C;
+                float* gv = bufv + ((size_t)(m0 + wrow0 + rr) * S + seg) * C;
+                int* gj = bufj + ((size_t)(m0 + wrow0 + rr) * S + seg) * C;
                 unsigned key[NE];
                 int ej[NE];
 #pragma unroll
@@ -328,60 +350,64 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
                 __syncwarp();
             }
         };
-        // The code of this loop is kept SMALL on purpose (one compaction site, one 16-column filter
-        // body looped four times): with a single warp per scheduler an instruction-cache miss is fully
-        // exposed, and the fully unrolled version (111 KB of SASS) spent most of its time in
-        // stall_no_inst.
+        // One 16-column group of the row: build the pass mask, and only if some row of the warp passes
+        // anything park the 16 values in shared memory (dynamic indexing) and append the passing ones.
+        // Passing entries are rare (~L per row per sweep once the threshold is warm), so the cost of a
+        // group is the 16 compares.
+        auto filter = [&](const uint32_t (&r)[16], int cbase) {
+            unsigned mask = 0u;
+#pragma unroll
+            for (int cc = 0; cc < 16; ++cc) mask |= (__uint_as_float(r[cc]) > thr) ? (1u << cc) : 0u;
+            const int lim = N - cbase;                               // columns >= lim are padding
+            if (lim < 16) mask &= lim <= 0 ? 0u : ((1u << lim) - 1u);
+            if (__any_sync(0xffffffffu, mask != 0u)) {
+#pragma unroll
+                for (int cc = 0; cc < 16; ++cc) pv[cc * TC_BM] = __uint_as_float(r[cc]);
+                while (mask) {
+                    const int cc = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    bv[cnt] = pv[cc * TC_BM];
+                    bj[cnt] = cbase + cc;
+                    ++cnt;
+                }
+                __syncwarp();
+            }
+        };
+        // The TMEM loads are software-pipelined one group ahead (two register sets); the loop body is
+        // kept small on purpose: with one warp per scheduler an instruction-cache miss is fully exposed.
         bool ok = true;
+        constexpr int NG = TC_BN / 16;
 #pragma unroll 1
-        for (int t = 0; t <= ntiles; ++t) {
-            // compaction point: once per tile (the tile can append at most 64), and once at the very end
-            const unsigned need = __ballot_sync(0xffffffffu, t == ntiles ? cnt > L : cnt + TC_BN > C);
+        for (int t = wg;; t += 2) {
+            // compaction point: once per tile (the tile can append at most TC_BN), and once at the very end
+            const bool last = t >= ntiles;
+            const unsigned need = __ballot_sync(0xffffffffu, last ? cnt > L : cnt + TC_BN > C);
             if (need) compact(need);
-            if (t == ntiles) break;
-            const int acc = t & 1;
+            if (last) break;
             const uint32_t aph = (uint32_t)(t >> 1) & 1u;
-            if (!mbar_wait(b_tfull + 8 * acc, aph, err, 5)) { ok = false; break; }
+            if (!mbar_wait(b_tfull + 8 * wg, aph, err, 5)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * TC_BN;
-            const int j0 = t * TC_BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + wg * TC_BN;
+            const int j0 = (tile0 + t) * TC_BN;
+            uint32_t ra[16], rb[16];
+            tmem_ld16(taddr, ra);
 #pragma unroll 1
-            for (int grp = 0; grp < 4; ++grp) {
-                uint32_t r[16];
-                tmem_ld16(taddr + grp * 16, r);
-                tmem_wait_ld();
-                if (grp == 3) {                                      // whole tile read: TMEM stage is free again
+            for (int grp = 0; grp < NG; grp += 2) {
+                tmem_wait_ld16(ra);
+                tmem_ld16(taddr + (grp + 1) * 16, rb);
+                if (!(dbg & 1)) filter(ra, j0 + grp * 16);
+                tmem_wait_ld16(rb);
+                if (grp + 2 < NG) {
+                    tmem_ld16(taddr + (grp + 2) * 16, ra);
+                } else {                                             // whole tile read: TMEM stage is free again
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(b_tempty + 8 * acc);
+                    if (lane == 0) mbar_arrive(b_tempty + 8 * wg);
                 }
-                if (dbg & 1) continue;
-                const int lim = N - j0 - grp * 16;                   // columns >= lim are padding
-                unsigned mask = 0u;
-#pragma unroll
-                for (int cc = 0; cc < 16; ++cc)
-                    mask |= ((cc < lim) & (__uint_as_float(r[cc]) > thr)) ? (1u << cc) : 0u;
-                const int np = __popc(mask);
-                if (__any_sync(0xffffffffu, mask != 0u)) {
-                    // branch-free staging: passing columns to consecutive slots, the rest to the trash slot
-#pragma unroll
-                    for (int cc = 0; cc < 16; ++cc) {
-                        const int slot = (mask >> cc) & 1u ? __popc(mask & ((1u << cc) - 1u)) : 16;
-                        pv[slot * TC_BM] = __uint_as_float(r[cc]);
-                        pj[slot * TC_BM] = j0 + grp * 16 + cc;
-                    }
-                    for (int q = 0; q < np; ++q) {
-                        bv[cnt + q] = pv[q * TC_BM];
-                        bj[cnt + q] = pj[q * TC_BM];
-                    }
-                    cnt += np;
-                }
+                if (!(dbg & 1)) filter(rb, j0 + (grp + 1) * 16);
             }
         }
-        if (ok && m0 + row < N) {
-            rowcnt[m0 + row] = cnt;
-            if (cnt < L) flags[(m0 + row) / 64] = 1;                 // stale hint: exact fix-up
-        }
+        if (ok && m0 + row < N) rowcnt[(size_t)(m0 + row) * S + seg] = cnt;
     }
     tc_fence_before();
     __syncthreads();
@@ -394,33 +420,121 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------
 // 3. exact re-score + ranking of the candidates (one warp per row)
 // ---------------------------------------------------------------------------------------
-constexpr int RS_WARPS = 4;
+constexpr int RS_WARPS = 2;
+constexpr int RS_MAXSEL = 96;      // candidates re-scored per row: L <= n <= L + 8 <= 96
+// order-preserving float <-> unsigned key
+__device__ __forceinline__ unsigned f2key(float f) {
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu)); }
+
 template <int D>
 __global__ void __launch_bounds__(RS_WARPS * 32)
-k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int K, int L, int C,
+k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int K, int L, int C, int S,
           const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ rowcnt,
           float* __restrict__ kth_out,
           int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, int* __restrict__ block_flags) {
-    __shared__ float s_cos[RS_WARPS][TC_MAXL];
-    __shared__ int s_j[RS_WARPS][TC_MAXL];
+    __shared__ unsigned long long s_key[RS_WARPS][RS_MAXSEL];  // ranking keys (exact cosine, index)
+    __shared__ float s_av[RS_WARPS][RS_MAXSEL];             // approximate (tensor-core) values of the selection
+    __shared__ int s_j[RS_WARPS][RS_MAXSEL];
     __shared__ int s_out[RS_WARPS][TC_MAXL];
-    extern __shared__ __align__(16) float rs_smem[];        // per warp: candidate tile [32][D+4] + v_i [D]
+    extern __shared__ __align__(16) float rs_smem[];        // per warp: tile [32][D+4] (first the pool keys/idx [2][S*L]), v_i [D]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int i = blockIdx.x * RS_WARPS + wid;
     if (i >= N) return;
     constexpr int TS = D + 4;                                    // tile row stride: conflict-free float4 row reads
     float* tile = rs_smem + (size_t)wid * (32 * TS + D);
     float* svi = tile + 32 * TS;
+    unsigned* pk = reinterpret_cast<unsigned*>(tile);        // the pool is dead before the tile is first written
+    int* pj = reinterpret_cast<int*>(pk + S * L);
     for (int d = 4 * lane; d < D; d += 128)
         *reinterpret_cast<float4*>(svi + d) = __ldg(reinterpret_cast<const float4*>(V + (size_t)i * D + d));
     const float ni = nrm[i];
-    const int have = rowcnt[i];
     for (int k = lane; k < K; k += 32) s_out[wid][k] = i;     // placeholder if the row is short (it is flagged)
+    // ---- merge the row's candidate segments: the L best approximate values of their union ----
+    // (segment counts first, then one flat pass over all segments so that every load is independent)
+    int my_cnt = lane < S ? min(rowcnt[(size_t)i * S + lane], L) : 0;     // S <= 2 * TC_MAXSPLIT <= 32
+    int my_off = my_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, my_off, o);
+        if (lane >= o) my_off += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, my_off, 31);
+    my_off -= my_cnt;                                                     // exclusive prefix
+    for (int f0 = 0; f0 < S * L; f0 += 32) {
+        const int f = f0 + lane;
+        const int sg = min(f / L, S - 1), e = f - sg * L;
+        const int c = __shfl_sync(0xffffffffu, my_cnt, sg), off = __shfl_sync(0xffffffffu, my_off, sg);
+        if (e < c) {
+            const size_t src = ((size_t)i * S + sg) * C + e;
+            pk[off + e] = f2key(__ldg(cand_val + src));
+            pj[off + e] = __ldg(cand_idx + src);
+        }
+    }
     __syncwarp();
+    // Selection by approximate value: any T with L <= #{key >= T} <= Lmax = L + 8 will do (every extra
+    // candidate is another 4*D bytes through L2, which is what bounds this kernel).  Bisection on the
+    // key bits below the common prefix of the pool, two bits per step, stops at the first such T --
+    // a handful of steps; only a tie cluster straddling the window runs to the last bit.
+    const int Lmax = min(RS_MAXSEL, L + 8);
+    int have = total;
+    if (total <= Lmax) {
+        for (int e = lane; e < total; e += 32) { s_av[wid][e] = key2f(pk[e]); s_j[wid][e] = pj[e]; }
+    } else {
+        unsigned kmx = 0u, kmn = 0xffffffffu;
+        for (int e = lane; e < total; e += 32) { const unsigned k = pk[e]; kmx = max(kmx, k); kmn = min(kmn, k); }
+        kmx = __reduce_max_sync(0xffffffffu, kmx);
+        kmn = __reduce_min_sync(0xffffffffu, kmn);
+        int bit = (31 - __clz((kmx ^ kmn) | 1u)) & ~1;                    // highest differing bit pair
+        unsigned T = bit >= 30 ? 0u : (kmx >> (bit + 2)) << (bit + 2);   // common prefix
+        int nT = total;                                                   // #{key >= T}
+#pragma unroll 1
+        for (; bit >= 0 && nT > Lmax; bit -= 2) {
+            const unsigned c1 = T | (1u << bit), c2 = T | (2u << bit), c3 = T | (3u << bit);
+            unsigned c = 0;                                               // three counts (< 1024 each), 10 bits apiece
+            for (int e = lane; e < total; e += 32) {
+                const unsigned k = pk[e];
+                c += (k >= c1 ? 1u : 0u) + (k >= c2 ? 1u << 10 : 0u) + (k >= c3 ? 1u << 20 : 0u);
+            }
+            c = __reduce_add_sync(0xffffffffu, c);
+            const int n1 = c & 1023, n2 = (c >> 10) & 1023, n3 = c >> 20;
+            if (n3 >= L) { T = c3; nT = n3; }
+            else if (n2 >= L) { T = c2; nT = n2; }
+            else if (n1 >= L) { T = c1; nT = n1; }
+        }
+        // keep keys > T, and keys == T in position order while there is room (nT <= Lmax: all of them)
+        int n_gt = 0;
+        for (int e = lane; e < total; e += 32) n_gt += pk[e] > T;
+        n_gt = __reduce_add_sync(0xffffffffu, n_gt);
+        const int need_eq = min(nT, Lmax) - n_gt;
+        const unsigned lt = (1u << lane) - 1u;
+        int eq_before = 0, kept_before = 0;
+        for (int e0 = 0; e0 < total; e0 += 32) {
+            const int e = e0 + lane;
+            const unsigned k = e < total ? pk[e] : 0u;
+            const bool is_eq = e < total && k == T;
+            const unsigned eqm = __ballot_sync(0xffffffffu, is_eq);
+            const bool keep = e < total && (k > T || (is_eq && eq_before + __popc(eqm & lt) < need_eq));
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int slot = kept_before + __popc(km & lt);
+                s_av[wid][slot] = key2f(k);
+                s_j[wid][slot] = pj[e];
+            }
+            eq_before += __popc(eqm);
+            kept_before += __popc(km);
+        }
+        have = kept_before;
+    }
+    if (lane == 0 && have < L) block_flags[i / 64] = 1;       // stale warm-start hint: exact fix-up
+    __syncwarp();
+    // ---- exact re-score, 32 candidates at a time ----
     float amin = INFINITY;
-    for (int l0 = 0; l0 < L; l0 += 32) {
+    for (int l0 = 0; l0 < have; l0 += 32) {
         const int l = l0 + lane;
-        const int j = (l < L && l < have) ? cand_idx[(size_t)i * C + l] : -1;
+        const int j = l < have ? s_j[wid][l] : -1;
         // stage the 32 candidate rows with coalesced 16-byte loads, 8 loads in flight per lane
         constexpr int LPR = D / 4, RPP = 32 / LPR;            // lanes per row, rows per warp-wide load
         const int sub = lane / LPR, dq = 4 * (lane % LPR);
@@ -438,61 +552,71 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int
                 *reinterpret_cast<float4*>(tile + (c0 + u * RPP + sub) * TS + dq) = r[u];
         }
         __syncwarp();
-        if (l < L) {
-            float c = -INFINITY;
-            if (j >= 0) {
-                // one fmaf chain over d = 0..D-1, exactly as graph_build.cu accumulates it
-                const float4* vj4 = reinterpret_cast<const float4*>(tile + lane * TS);
-                const float4* vi4 = reinterpret_cast<const float4*>(svi);
-                float dot = 0.f;
+        if (j >= 0) {
+            // one fmaf chain over d = 0..D-1, exactly as graph_build.cu accumulates it
+            const float4* vj4 = reinterpret_cast<const float4*>(tile + lane * TS);
+            const float4* vi4 = reinterpret_cast<const float4*>(svi);
+            float dot = 0.f;
 #pragma unroll 8
-                for (int q = 0; q < D / 4; ++q) {
-                    const float4 a = vi4[q], b = vj4[q];
-                    dot = fmaf(a.x, b.x, dot);
-                    dot = fmaf(a.y, b.y, dot);
-                    dot = fmaf(a.z, b.z, dot);
-                    dot = fmaf(a.w, b.w, dot);
-                }
-                c = dot / (ni * nrm[j]);
+            for (int q = 0; q < D / 4; ++q) {
+                const float4 a = vi4[q], b = vj4[q];
+                dot = fmaf(a.x, b.x, dot);
+                dot = fmaf(a.y, b.y, dot);
+                dot = fmaf(a.z, b.z, dot);
+                dot = fmaf(a.w, b.w, dot);
             }
-            s_cos[wid][l] = c;
-            s_j[wid][l] = j;
-            amin = fminf(amin, l < have ? cand_val[(size_t)i * C + l] : -INFINITY);
+            const float c = dot / (ni * nrm[j]);
+            // ranking key: exact cosine descending, then index ascending
+            s_key[wid][l] = ((unsigned long long)f2key(c) << 32) | (unsigned long long)(0xffffffffu - (unsigned)j);
+            amin = fminf(amin, s_av[wid][l]);
         }
         __syncwarp();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o));
     int above = 0;
-    for (int l = lane; l < L && l < have; l += 32) above += cand_val[(size_t)i * C + l] > amin + 2.f * TC_EPS ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+    for (int l = lane; l < have; l += 32) above += s_av[wid][l] > amin + 2.f * TC_EPS ? 1 : 0;
+    above = __reduce_add_sync(0xffffffffu, above);
     if (lane == 0 && above < K) block_flags[i / 64] = 1;      // the slack window is ambiguous: exact fix-up
     __syncwarp();
-    for (int l = lane; l < L; l += 32) {
-        const float c = s_cos[wid][l];
-        const int j = s_j[wid][l];
-        int rank = 0;
-        for (int q = 0; q < L; ++q) {
-            const float cq = s_cos[wid][q];
-            const int jq = s_j[wid][q];
-            rank += (int)(cq > c) | ((int)(cq == c) & (int)(jq < j));
+    // ---- rank = number of larger keys; a lane ranks its (up to three) candidates in one sweep ----
+    {
+        unsigned long long k0 = lane < have ? s_key[wid][lane] : ~0ull;
+        unsigned long long k1 = lane + 32 < have ? s_key[wid][lane + 32] : ~0ull;
+        unsigned long long k2 = lane + 64 < have ? s_key[wid][lane + 64] : ~0ull;
+        int r0 = 0, r1 = 0, r2 = 0;
+        for (int q = 0; q < have; ++q) {
+            const unsigned long long kq = s_key[wid][q];
+            r0 += kq > k0; r1 += kq > k1; r2 += kq > k2;
         }
-        if (j >= 0 && rank < K) s_out[wid][rank] = j;
-        if (j >= 0 && rank == K - 1 && kth_out != nullptr) kth_out[i] = c;
+        const unsigned long long ks[3] = {k0, k1, k2};
+        const int rs[3] = {r0, r1, r2};
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int l = lane + 32 * u;
+            if (l < have && rs[u] < K) {
+                s_out[wid][rs[u]] = (int)(0xffffffffu - (unsigned)(ks[u] & 0xffffffffull));
+                if (rs[u] == K - 1 && kth_out != nullptr) kth_out[i] = key2f((unsigned)(ks[u] >> 32));
+            }
+        }
     }
     __syncwarp();
     if (idx_out != nullptr)
         for (int k = lane; k < K; k += 32) idx_out[(size_t)i * K + k] = (int64_t)s_out[wid][k];
-    if (nbr_out != nullptr && lane == 0) {
+    if (nbr_out != nullptr) {
+        // neighbour list: the top-k without the row itself, then the row itself, then -1 padding
         int32_t* nb = nbr_out + (size_t)i * (K + 1);
+        const unsigned lt = (1u << lane) - 1u;
         int o = 0;
-        for (int k = 0; k < K; ++k) {
-            const int j = s_out[wid][k];
-            if (j != i) nb[o++] = j;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            const int j = k < K ? s_out[wid][k] : i;
+            const unsigned m = __ballot_sync(0xffffffffu, j != i);
+            if (j != i) nb[o + __popc(m & lt)] = j;
+            o += __popc(m);
         }
-        nb[o++] = i;
-        for (; o < K + 1; ++o) nb[o] = -1;
+        if (lane == 0) nb[o] = i;
+        for (int k = o + 1 + lane; k < K + 1; k += 32) nb[k] = -1;
     }
 }
 
@@ -515,14 +639,27 @@ bool gram_tc_supported(int N, int D, int K) {
     return N >= 1024 && (D == 64 || D == 128) && K + TC_SLACK <= TC_MAXL && K + TC_SLACK <= N;
 }
 
+// column splits per row block: fill the SMs when there are few row blocks (N = 4096 -> 32 blocks x 4)
+static void tc_split(int N, int* nsplit, int* tiles_per_split) {
+    const int blocks = ceil_div(N, TC_BM), ntiles = ceil_div(N, TC_BN);
+    int want = num_sms() / blocks;
+    if (want < 1) want = 1;
+    if (want > TC_MAXSPLIT) want = TC_MAXSPLIT;
+    const int tps = ceil_div(ntiles, want);
+    *tiles_per_split = tps;
+    *nsplit = ceil_div(ntiles, tps);
+}
+
 size_t gram_tc_ws_bytes(int N, int D, int K) {
     const int C = TC_MAXC;
     (void)K;
-    const size_t Npad = (size_t)ceil_div(N, TC_BM) * TC_BM;
+    int nsplit, tps;
+    tc_split(N, &nsplit, &tps);
+    const size_t Npad = (size_t)ceil_div(N, TC_BM) * TC_BM, S = 2 * (size_t)nsplit;
     size_t b = align_up((size_t)N * sizeof(float), 256);
     b += 2 * align_up((size_t)N * D * sizeof(__nv_bfloat16), 256);
-    b += 2 * align_up(Npad * C * sizeof(float), 256);
-    b += align_up((size_t)N * sizeof(int), 256);
+    b += 2 * align_up(Npad * S * C * sizeof(float), 256);
+    b += align_up(Npad * S * sizeof(int), 256);
     b += align_up(((size_t)(N + 63) / 64 + 68) * sizeof(int), 256);
     return b;
 }
@@ -530,14 +667,17 @@ size_t gram_tc_ws_bytes(int N, int D, int K) {
 int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, cudaStream_t st,
                    float* kth, float margin, float** nrm_out, int** flags_out) {
     const int L = K + TC_SLACK, C = TC_MAXC, KB = D / TC_BK;
+    int nsplit, tps;
+    tc_split(N, &nsplit, &tps);
+    const int S = 2 * nsplit;
     const size_t Npad = (size_t)ceil_div(N, TC_BM) * TC_BM;
     char* p = (char*)ws;
     float* nrm = (float*)p;                 p += align_up((size_t)N * sizeof(float), 256);
     __nv_bfloat16* hi = (__nv_bfloat16*)p;  p += align_up((size_t)N * D * sizeof(__nv_bfloat16), 256);
     __nv_bfloat16* lo = (__nv_bfloat16*)p;  p += align_up((size_t)N * D * sizeof(__nv_bfloat16), 256);
-    float* bufv = (float*)p;                p += align_up(Npad * C * sizeof(float), 256);
-    int* bufj = (int*)p;                    p += align_up(Npad * C * sizeof(float), 256);
-    int* rowcnt = (int*)p;                  p += align_up((size_t)N * sizeof(int), 256);
+    float* bufv = (float*)p;                p += align_up(Npad * S * C * sizeof(float), 256);
+    int* bufj = (int*)p;                    p += align_up(Npad * S * C * sizeof(float), 256);
+    int* rowcnt = (int*)p;                  p += align_up(Npad * S * sizeof(int), 256);
     int* flags = (int*)p;                   // [ceil(N/64)] block flags, then the error word
     const int nblk64 = (N + 63) / 64;
     int* err = flags + nblk64;
@@ -562,22 +702,23 @@ int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* n
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     GDN_CHECK_ARG(r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
 
-    const size_t smem = 1024 + (size_t)2 * KB * TC_BM * 128 + (size_t)TC_STAGES * 2 * KB * TC_BN * 128 +
-                        (size_t)2 * 17 * TC_BM * sizeof(float) + (4 + 2 * TC_STAGES + 4) * 8 + 16;
+    const size_t smem = 1024 + (size_t)2 * KB * TC_BM * 128 + (size_t)TC_STAGES * 2 * TC_BN * 128 +
+                        (size_t)2 * 16 * TC_BM * sizeof(float) + (4 + 2 * TC_STAGES + 4) * 8 + 16;
     GDN_CHECK_ARG(smem <= 227 * 1024, "gram_tc: %zu bytes of shared memory needed", smem);
     e = ensure_dyn_smem(k_gram_tc, smem);
     if (e != cudaSuccess) return cuda_fail(e, "smem attr k_gram_tc");
     static int dbg = -1;
     if (dbg < 0) { const char* e_ = getenv("GDN_TC_DBG"); dbg = e_ ? atoi(e_) : 0; }
-    k_gram_tc<<<ceil_div(N, TC_BM), 256, smem, st>>>(tm_hi, tm_lo, N, KB, L, C, bufv, bufj, rowcnt, kth, margin, flags,
-                                                     err, dbg);
+    k_gram_tc<<<dim3(ceil_div(N, TC_BM), nsplit), TC_THREADS, smem, st>>>(tm_hi, tm_lo, N, KB, L, C, tps, bufv, bufj, rowcnt,
+                                                                          kth, margin, err, dbg);
     GDN_CHECK_LAUNCH("k_gram_tc");
+    GDN_CHECK_ARG(2 * S * L <= 32 * (D + 4), "gram_tc: candidate pool (%d) exceeds the re-score tile", 2 * S * L);
     const size_t rs_smem = (size_t)RS_WARPS * (32 * (D + 4) + D) * sizeof(float);
     auto rescore = D == 128 ? k_rescore<128> : k_rescore<64>;
     e = ensure_dyn_smem_ptr(reinterpret_cast<const void*>(rescore), rs_smem);
     if (e != cudaSuccess) return cuda_fail(e, "smem attr k_rescore");
-    rescore<<<ceil_div(N, RS_WARPS), RS_WARPS * 32, rs_smem, st>>>(V, nrm, N, K, L, C, bufv, bufj, rowcnt, kth, idx, nbr,
-                                                                  flags);
+    rescore<<<ceil_div(N, RS_WARPS), RS_WARPS * 32, rs_smem, st>>>(V, nrm, N, K, L, C, S, bufv, bufj, rowcnt, kth, idx,
+                                                                  nbr, flags);
     GDN_CHECK_LAUNCH("k_rescore");
     *nrm_out = nrm;
     *flags_out = flags;

@@ -21,11 +21,9 @@ def build(V, K, tc):
     return idx, nbr, ws
 
 def flags_of(ws, N, D, K):
-    C = 256
     al = lambda v: (v + 255) // 256 * 256
-    npad = (N + 127) // 128 * 128
-    off = al(N * 4) + 2 * al(N * D * 2) + 2 * al(npad * C * 4) + al(N * 4)
     nblk = (N + 63) // 64
+    off = lib.gdn_graph_build_ws_bytes(N, D, K) - al((nblk + 68) * 4)     # flags + error word close the TC workspace
     w = ws[off:off + (nblk + 4) * 4].view(torch.int32).cpu()
     return int(w[:nblk].sum()), int(w[nblk])
 
