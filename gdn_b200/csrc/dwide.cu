@@ -16,6 +16,7 @@
 // in registers and the embedding gradient needs no atomics.
 #include "common.cuh"
 #include "launchers.h"
+#include "mma_tf32.cuh"
 
 namespace gdn {
 
@@ -360,6 +361,199 @@ k_lin_bwd(const float* __restrict__ gout, const float* __restrict__ A, const flo
         }
         __syncthreads();
     }
+}
+
+// Tensor-core contractions of the lin backward for D in {64, 128}, W <= 16 (mma.sync m16n8k8, 3xTF32),
+// shared by k_lin_bwd_mma (module boundary) and k_bwd3_mma (fused head).  On a tile of TR = 16 rows,
+// G [16 x D] (fp32, row stride D + 4) and A [16 x WP] (row stride WP + 4) in shared memory:
+//   (1) g_A tile [16 x WP]   = G . Wl            (A fragments by ldmatrix, Wl pre-split {hi, lo} in smem)
+//   (2) g_Wl^T  [WP x D]    += A^T . G           (accumulators stay in registers for the whole kernel)
+// The k index of (2) walks the rows in the order 0,2,4,6,1,3,5,7 so that the B-fragment reads of G are
+// bank-conflict free with the same row stride that makes the ldmatrix reads of (1) conflict free.
+template <int DPL, int WP>
+struct LinBwdMma {
+    static constexpr int DT = DPL * 32, GS = DT + 4, TR = 16;
+    static constexpr int WS = WP + 4;             // Wl row stride in 8-byte {hi, lo} pairs: conflict-free LDS.64
+    static constexpr int AS = RowStage<WP>::STRIDE;
+    static constexpr int NT1 = WP / 8, NT2 = DT / 8;
+    static_assert(WP == 8 || WP == 16, "LinBwdMma: W <= 16");
+    static_assert(DPL == 2 || DPL == 4, "LinBwdMma: D in {64, 128}");
+    static constexpr size_t W_BYTES = (size_t)DT * WS * sizeof(uint2);
+    static constexpr size_t G_BYTES = (size_t)TR * GS * sizeof(float);
+    static constexpr size_t RED_BYTES = (size_t)8 * (WP + 1) * DT * sizeof(float);
+
+    // all threads of the CTA; caller synchronises
+    __device__ __forceinline__ static void fill_w(uint2* sW, const float* __restrict__ Wl, int W) {
+        for (int e = threadIdx.x; e < DT * WP; e += blockDim.x) {
+            const int d = e / WP, w = e % WP;
+            uint2 v;
+            split_tf32(w < W ? Wl[(size_t)d * W + w] : 0.f, v.x, v.y);
+            sW[d * WS + w] = v;
+        }
+    }
+    // (1): c1[nt] holds rows (g, g + 8) x columns (8 nt + 2t, + 1) of the tile's g_A
+    __device__ __forceinline__ static void ga_tile(const float* sG, const uint2* sW, int lane, float (&c1)[NT1][4]) {
+        const int g = lane >> 2, t = lane & 3;
+        // ldmatrix row address: matrix j = lane >> 3 -> rows (j & 1) * 8 + (lane & 7), columns + (j >> 1) * 4
+        const float* ldm = sG + (((lane >> 3) & 1) * 8 + (lane & 7)) * GS + (lane >> 4) * 4;
+        const uint2* wb = sW + t * WS + g;
+        float c0[NT1][4];                         // two accumulator sets: shorter dependent MMA chains
+#pragma unroll
+        for (int nt = 0; nt < NT1; ++nt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c0[nt][q] = c1[nt][q] = 0.f;
+#pragma unroll 2
+        for (int ks = 0; ks < DT / 8; ks += 2) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                uint32_t raw[4], ah[4], al[4];
+                ldmatrix_x4(raw, ldm + 8 * (ks + u));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_tf32(__uint_as_float(raw[q]), ah[q], al[q]);
+#pragma unroll
+                for (int nt = 0; nt < NT1; ++nt) {
+                    const uint2 b0 = wb[(8 * (ks + u)) * WS + 8 * nt];
+                    const uint2 b1 = wb[(8 * (ks + u) + 4) * WS + 8 * nt];
+                    if (u == 0) mma_3xtf32(c0[nt], ah, al, b0.x, b1.x, b0.y, b1.y);
+                    else mma_3xtf32(c1[nt], ah, al, b0.x, b1.x, b0.y, b1.y);
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT1; ++nt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c1[nt][q] += c0[nt][q];
+    }
+    // (2): acc2[nt] holds rows w = (g, g + 8) x columns d = (8 nt + 2t, + 1) of g_Wl^T
+    __device__ __forceinline__ static void gwl_acc(const float* sG, const float* sa, int lane, float (&acc2)[NT2][4]) {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int ks = 0; ks < TR / 8; ++ks) {
+            const int ra = 8 * ks + 2 * t, rb = ra + 1;
+            uint32_t ah[4], al[4];
+            split_tf32(sa[ra * AS + g], ah[0], al[0]);
+            split_tf32(sa[rb * AS + g], ah[2], al[2]);
+            if (WP == 16) {
+                split_tf32(sa[ra * AS + g + 8], ah[1], al[1]);
+                split_tf32(sa[rb * AS + g + 8], ah[3], al[3]);
+            } else {
+                ah[1] = al[1] = ah[3] = al[3] = 0u;
+            }
+            const float* ga = sG + ra * GS + g;
+#pragma unroll
+            for (int nt = 0; nt < NT2; ++nt) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32(ga[8 * nt], bh0, bl0);
+                split_tf32(ga[GS + 8 * nt], bh1, bl1);
+                mma_3xtf32(acc2[nt], ah, al, bh0, bh1, bl0, bl1);
+            }
+        }
+    }
+    // cross-warp reduction of acc2 and the per-lane bias-gradient sums into the CTA's part record
+    // [D*W + D] doubles; red = [8][WP + 1][DT] floats of scratch; caller has synchronised the CTA
+    __device__ __forceinline__ static void reduce(const float (&acc2)[NT2][4], const float (&gb)[DPL], float* red, int W,
+                                                  double* __restrict__ prec) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int nt = 0; nt < NT2; ++nt) {
+            const int d0 = 8 * nt + 2 * t;
+            float* r0 = red + ((size_t)wid * (WP + 1) + g) * DT + d0;
+            r0[0] = acc2[nt][0];
+            r0[1] = acc2[nt][1];
+            if (WP == 16) {
+                r0[8 * DT] = acc2[nt][2];
+                r0[8 * DT + 1] = acc2[nt][3];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) red[((size_t)wid * (WP + 1) + WP) * DT + lane * DPL + j] = gb[j];
+        __syncthreads();
+        for (int e = threadIdx.x; e < (WP + 1) * DT; e += blockDim.x) {
+            const int w = e / DT, d = e % DT;
+            if (w < W || w == WP) {
+                double s = 0.0;
+                for (int q = 0; q < nw; ++q) s += (double)red[((size_t)q * (WP + 1) + w) * DT + d];
+                if (w == WP) prec[(size_t)DT * W + d] = s;
+                else prec[(size_t)d * W + w] = s;
+            }
+        }
+    }
+};
+
+// module boundary, tensor-core version: a warp stages 16 rows of g_out and of A per tile.
+// dynamic smem: Wl {hi,lo} [D][WP+4] | per warp: G tile [16][D+4], A tile [16][WP+4]; reduction scratch aliases it.
+template <int DPL, int WP>
+__global__ void __launch_bounds__(256, 2)
+k_lin_bwd_mma(const float* __restrict__ gout, const float* __restrict__ A, const float* __restrict__ Wl,
+              long long n, int W, int D, float* __restrict__ gA, double* __restrict__ part) {
+    using M = LinBwdMma<DPL, WP>;
+    constexpr int TR = M::TR, GS = M::GS, AS = M::AS;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const long long warp = (long long)blockIdx.x * nw + wid;
+    const long long nwarps = (long long)gridDim.x * nw;
+    uint2* sW = reinterpret_cast<uint2*>(dyn_smem);
+    float* sG = reinterpret_cast<float*>(dyn_smem + M::W_BYTES) + (size_t)wid * (TR * GS + TR * AS);
+    float* sa = sG + TR * GS;
+    M::fill_w(sW, Wl, W);
+    __syncthreads();
+    float acc2[M::NT2][4], gb[DPL];
+#pragma unroll
+    for (int nt = 0; nt < M::NT2; ++nt) acc2[nt][0] = acc2[nt][1] = acc2[nt][2] = acc2[nt][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) gb[j] = 0.f;
+    for (long long r0 = warp * TR; r0 < n; r0 += nwarps * TR) {
+        const int nb = (int)((n - r0) < TR ? (n - r0) : TR);
+        __syncwarp();
+        if (lane < TR) {                                                      // A rows (zero beyond the tail)
+            float* dst = sa + lane * AS;
+            const float* row = A + (size_t)(r0 + lane) * W;
+            if (lane < nb && (W & 3) == 0) {
+#pragma unroll
+                for (int w = 0; w < WP; w += 4) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (w < W) v = __ldg(reinterpret_cast<const float4*>(row + w));
+                    *reinterpret_cast<float4*>(dst + w) = v;
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < WP; ++w) dst[w] = (lane < nb && w < W) ? __ldg(row + w) : 0.f;
+            }
+        }
+#pragma unroll 8
+        for (int rr = 0; rr < TR; ++rr) {                                     // G rows, coalesced
+            float go[DPL];
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) go[j] = 0.f;
+            if (rr < nb) load_chan_vec<DPL>(gout + (size_t)(r0 + rr) * D, lane, go);
+            store_chan<DPL>(sG + rr * GS, lane, go);
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) gb[j] += go[j];
+        }
+        __syncwarp();
+        float c1[M::NT1][4];
+        M::ga_tile(sG, sW, lane, c1);
+#pragma unroll
+        for (int nt = 0; nt < M::NT1; ++nt) {
+            const int w0 = 8 * nt + 2 * t;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int rr = g + 8 * hh;
+                if (rr < nb && w0 < W) {
+                    float* o = gA + (size_t)(r0 + rr) * W + w0;
+                    if ((W & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(c1[nt][2 * hh], c1[nt][2 * hh + 1]);
+                    else {
+                        o[0] = c1[nt][2 * hh];
+                        if (w0 + 1 < W) o[1] = c1[nt][2 * hh + 1];
+                    }
+                }
+            }
+        }
+        M::gwl_acc(sG, sa, lane, acc2);
+    }
+    __syncthreads();
+    M::reduce(acc2, gb, reinterpret_cast<float*>(dyn_smem), W, part + (size_t)blockIdx.x * ((size_t)D * W + D));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -881,6 +1075,103 @@ k_bwd3(HeadArgs h, BwdArgs g, double* __restrict__ part) {
     }
 }
 
+// pass 3, tensor-core version (saved xh1, D in {64, 128}, W <= 16): per batch of 16 windows the warp
+// first walks the rows lane <-> channels (the BatchNorm/ReLU chain down to g_z, g_bias partials) and parks
+// g_z [16 x D] in shared memory, then runs the two contractions of LinBwdMma on that tile.
+// dynamic smem: per warp A tile + xh1 tile (as the other passes) | Wl {hi,lo} | per warp g_z tile [16][D+4]
+template <int DPL, int WP>
+__global__ void __launch_bounds__(256)
+k_bwd3_mma(HeadArgs h, BwdArgs g, double* __restrict__ part) {
+    constexpr bool NEED_A_ = true, BUF_ = true;
+    using M = LinBwdMma<DPL, WP>;
+    static_assert(M::TR == XH_ROWS, "tile rows = rows per buffered batch");
+    constexpr int GS = M::GS, AS = M::AS, TR = M::TR;
+    RowEval<DPL, WP> re;
+    BwdRow<DPL, WP> br;
+    re.init(h, threadIdx.x & 31, false);
+    br.init(h, threadIdx.x & 31);
+    const int wid = threadIdx.x >> 5;
+    float cB2[DPL], cG2[DPL], s2c[DPL], cB1[DPL], cG1[DPL], s1c[DPL];
+    {
+        const int ln = threadIdx.x & 31;
+        load_chan<DPL>(g.c2, ln, cB2);
+        load_chan<DPL>(g.c2 + h.D, ln, cG2);
+        load_chan<DPL>(g.c1, ln, cB1);
+        load_chan<DPL>(g.c1 + h.D, ln, cG1);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) { s2c[j] = br.g2[j] * br.k2a[j]; s1c[j] = re.g1[j] * re.k1a[j]; }
+    }
+    constexpr size_t STAGE_FLOATS = (size_t)8 * (RowStage<WP>::WARP_FLOATS + XhStage<DPL>::WARP_FLOATS);
+    uint2* sW = reinterpret_cast<uint2*>(reinterpret_cast<float*>(dyn_smem) + STAGE_FLOATS);
+    float* sG = reinterpret_cast<float*>(dyn_smem + STAGE_FLOATS * sizeof(float) + M::W_BYTES) + (size_t)wid * TR * GS;
+    M::fill_w(sW, h.Wl, h.W);
+    __syncthreads();
+    float acc2[M::NT2][4], gb[DPL];
+#pragma unroll
+    for (int nt = 0; nt < M::NT2; ++nt) acc2[nt][0] = acc2[nt][1] = acc2[nt][2] = acc2[nt][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) gb[j] = 0.f;
+    GDN_TASK_LOOP_BEGIN(h)
+        float v[DPL];
+        load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
+        GDN_BATCH_LOOP_BEGIN(h)
+            BwdSide<DPL> side;
+            side.load(h, g.gpred, i, b0, nb, lane);
+#pragma unroll 2
+            for (int rr = 0; rr < nb; ++rr) {
+                float a[WP], xh1[DPL], y1[DPL], kf[DPL], gz[DPL];
+                row_inputs<DPL, WP, false, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
+                const float gp = side.row(h, rr, lane, kf);
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) {
+                    const float p = fmaxf(y1[j], 0.f) * v[j];
+                    const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
+                    const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
+                    const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
+                    const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);
+                    const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
+                    gz[j] = s1c[j] * (gy1 - cB1[j] - xh1[j] * cG1[j]);            // d loss / d z
+                    gb[j] += gz[j];
+                }
+                store_chan<DPL>(sG + rr * GS, lane, gz);
+            }
+            if (nb < TR) {                                                        // tail: zero rows for the MMAs
+                float z[DPL];
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) z[j] = 0.f;
+                for (int rr = nb; rr < TR; ++rr) store_chan<DPL>(sG + rr * GS, lane, z);
+                for (int e = lane; e < (TR - nb) * AS; e += 32) sa_[nb * AS + e] = 0.f;
+            }
+            __syncwarp();
+            float c1[M::NT1][4];
+            M::ga_tile(sG, sW, lane, c1);
+            {
+                const int gg = lane >> 2, t = lane & 3;
+#pragma unroll
+                for (int nt = 0; nt < M::NT1; ++nt) {
+                    const int w0 = 8 * nt + 2 * t;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int rr = gg + 8 * hh;
+                        if (rr < nb && w0 < h.W) {
+                            float* o = g.gA + ((size_t)(b0 + rr) * h.N + i) * h.W + w0;
+                            if ((h.W & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(c1[nt][2 * hh], c1[nt][2 * hh + 1]);
+                            else {
+                                o[0] = c1[nt][2 * hh];
+                                if (w0 + 1 < h.W) o[1] = c1[nt][2 * hh + 1];
+                            }
+                        }
+                    }
+                }
+            }
+            M::gwl_acc(sG, sa_, lane, acc2);
+            __syncwarp();
+        GDN_BATCH_LOOP_END
+    GDN_TASK_LOOP_END
+    __syncthreads();
+    M::reduce(acc2, gb, reinterpret_cast<float*>(dyn_smem), h.W, part + (size_t)blockIdx.x * ((size_t)h.D * h.W + h.D));
+}
+
 // ---------------------------------------------------------------------------------------
 // per-CTA partial records -> one record of doubles (fixed summation order: deterministic)
 // block (32, 8): x <-> entry, y strides the records; grid = ceil(rec / 32)
@@ -1147,8 +1438,31 @@ int launch_lin_fwd(const Shape& s, const float* A, const gdn_layer_params* p, fl
     return 0;
 }
 
+template <int DPL, int WP>
+static int launch_lin_bwd_mma(const Shape& s, const float* gout, const float* A, const gdn_layer_params* p, float* gA,
+                              double* part, int* nrec, cudaStream_t st) {
+    using M = LinBwdMma<DPL, WP>;
+    constexpr int TR = M::TR, nw = 8;
+    const size_t tiles = M::W_BYTES + (size_t)nw * (M::G_BYTES + (size_t)TR * M::AS * 4);
+    const size_t smem = tiles > M::RED_BYTES ? tiles : M::RED_BYTES;
+    long long g = (s.n + (long long)TR * nw - 1) / ((long long)TR * nw);
+    if (g > 2 * num_sms()) g = 2 * num_sms();
+    const int grid = (int)(g < 1 ? 1 : g);
+    cudaError_t e = ensure_dyn_smem(k_lin_bwd_mma<DPL, WP>, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "smem attribute k_lin_bwd_mma");
+    k_lin_bwd_mma<DPL, WP><<<grid, nw * 32, smem, st>>>(gout, A, p->lin_weight, s.n, s.W, s.D, gA, part);
+    GDN_CHECK_LAUNCH("k_lin_bwd");
+    *nrec = grid;
+    return 0;
+}
+
 int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_layer_params* p, float* gA,
                    double* part, int* nrec, cudaStream_t st) {
+    // tensor-core path for the shapes it is built for
+    if (s.DPL == 4 && s.WP == 16) return launch_lin_bwd_mma<4, 16>(s, gout, A, p, gA, part, nrec, st);
+    if (s.DPL == 4 && s.WP == 8) return launch_lin_bwd_mma<4, 8>(s, gout, A, p, gA, part, nrec, st);
+    if (s.DPL == 2 && s.WP == 16) return launch_lin_bwd_mma<2, 16>(s, gout, A, p, gA, part, nrec, st);
+    if (s.DPL == 2 && s.WP == 8) return launch_lin_bwd_mma<2, 8>(s, gout, A, p, gA, part, nrec, st);
     // warps per CTA: as many as fit the shared-memory tiles
     int nw = 8;
     auto bytes = [&](int w) {
@@ -1277,9 +1591,30 @@ int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
     return 0;
 }
 
+template <int DPL, int WP>
+static int launch_bwd3_mma(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st) {
+    using M = LinBwdMma<DPL, WP>;
+    const size_t stage = (size_t)8 * (RowStage<WP>::WARP_FLOATS + XhStage<DPL>::WARP_FLOATS) * sizeof(float);
+    const size_t tiles = stage + M::W_BYTES + 8 * M::G_BYTES;
+    const size_t smem = tiles > M::RED_BYTES ? tiles : M::RED_BYTES;
+    // one resident CTA per SM (shared-memory bound): a persistent grid, each CTA walks its share of the tasks
+    int grid = dw_grid((long long)s.N * s.S);
+    const int per_sm = (int)((227 * 1024) / (smem + 1024));
+    const int cap = num_sms() * (per_sm < 1 ? 1 : per_sm);
+    if (grid > cap) grid = cap;
+    GDN_LAUNCH_DYN((k_bwd3_mma<DPL, WP>), grid, smem, st, h, g, part);
+    GDN_CHECK_LAUNCH("k_bwd3");
+    *nrec = grid;
+    return 0;
+}
+
 int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
     const bool buf = h.xh1 != nullptr;
+    if (buf && s.DPL == 4 && s.WP == 16) return launch_bwd3_mma<4, 16>(s, h, g, part, nrec, st);
+    if (buf && s.DPL == 4 && s.WP == 8) return launch_bwd3_mma<4, 8>(s, h, g, part, nrec, st);
+    if (buf && s.DPL == 2 && s.WP == 16) return launch_bwd3_mma<2, 16>(s, h, g, part, nrec, st);
+    if (buf && s.DPL == 2 && s.WP == 8) return launch_bwd3_mma<2, 8>(s, h, g, part, nrec, st);
 #define CALL(DPLC, WPC)                                                                                             \
     do {                                                                                                            \
         if (buf) GDN_LAUNCH_DYN((k_bwd3<DPLC, WPC, true>), grid, (dw_smem2<DPLC, WPC>(true, true, 0, true)), st, h, g, part); \
