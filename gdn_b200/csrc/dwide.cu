@@ -14,6 +14,7 @@
 // Thread mapping: lane <-> DPL = D/32 consecutive channels; a warp walks rows.  The fused
 // passes are sensor-major (a warp owns sensor i and a range of windows b), so V[i,:] stays
 // in registers and the embedding gradient needs no atomics.
+#include <stdlib.h>
 #include "common.cuh"
 #include "launchers.h"
 #include "mma_tf32.cuh"
@@ -380,14 +381,13 @@ struct LinBwdMma {
     static_assert(DPL == 2 || DPL == 4, "LinBwdMma: D in {64, 128}");
     static constexpr size_t W_BYTES = (size_t)DT * WS * sizeof(uint2);
     static constexpr size_t G_BYTES = (size_t)TR * GS * sizeof(float);
-    static constexpr size_t RED_BYTES = (size_t)8 * (WP + 1) * DT * sizeof(float);
 
     // all threads of the CTA; caller synchronises
     __device__ __forceinline__ static void fill_w(uint2* sW, const float* __restrict__ Wl, int W) {
         for (int e = threadIdx.x; e < DT * WP; e += blockDim.x) {
             const int d = e / WP, w = e % WP;
             uint2 v;
-            split_tf32(w < W ? Wl[(size_t)d * W + w] : 0.f, v.x, v.y);
+            split_tf32_rn(w < W ? Wl[(size_t)d * W + w] : 0.f, v.x, v.y);
             sW[d * WS + w] = v;
         }
     }
@@ -449,34 +449,40 @@ struct LinBwdMma {
             }
         }
     }
-    // cross-warp reduction of acc2 and the per-lane bias-gradient sums into the CTA's part record
-    // [D*W + D] doubles; red = [8][WP + 1][DT] floats of scratch; caller has synchronised the CTA
-    __device__ __forceinline__ static void reduce(const float (&acc2)[NT2][4], const float (&gb)[DPL], float* red, int W,
-                                                  double* __restrict__ prec) {
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // The tensor core adds into its fp32 accumulator with truncation, so a long chain of MMAs on one
+    // accumulator leaks towards zero (measured: 7e-5 on g_Wl after ~330 chained MMAs at C5).  The
+    // register accumulators are therefore flushed every 4 tiles into a CTA-wide fp32 image in shared
+    // memory (red.shared.add.f32, round-to-nearest) and restarted from zero.
+    static constexpr int ACS = DT + 8;                                    // accumulator image row stride
+    static constexpr size_t ACC_BYTES = (size_t)(WP + 1) * ACS * sizeof(float);
+    __device__ __forceinline__ static void zero_acc(float* sAcc) {        // all threads; caller synchronises
+        for (int e = threadIdx.x; e < (WP + 1) * ACS; e += blockDim.x) sAcc[e] = 0.f;
+    }
+    __device__ __forceinline__ static void flush(float (&acc2)[NT2][4], float* sAcc, int lane) {
         const int g = lane >> 2, t = lane & 3;
 #pragma unroll
         for (int nt = 0; nt < NT2; ++nt) {
-            const int d0 = 8 * nt + 2 * t;
-            float* r0 = red + ((size_t)wid * (WP + 1) + g) * DT + d0;
-            r0[0] = acc2[nt][0];
-            r0[1] = acc2[nt][1];
+            float* r0 = sAcc + g * ACS + 8 * nt + 2 * t;
+            atomicAdd(r0, acc2[nt][0]);
+            atomicAdd(r0 + 1, acc2[nt][1]);
             if (WP == 16) {
-                r0[8 * DT] = acc2[nt][2];
-                r0[8 * DT + 1] = acc2[nt][3];
+                atomicAdd(r0 + 8 * ACS, acc2[nt][2]);
+                atomicAdd(r0 + 8 * ACS + 1, acc2[nt][3]);
             }
+            acc2[nt][0] = acc2[nt][1] = acc2[nt][2] = acc2[nt][3] = 0.f;
         }
+    }
+    // end of kernel (every warp has flushed): bias-gradient partials join the image, which becomes the CTA's
+    // part record [D*W + D] doubles
+    __device__ __forceinline__ static void finish(const float (&gb)[DPL], float* sAcc, int W, double* __restrict__ prec) {
+        const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) red[((size_t)wid * (WP + 1) + WP) * DT + lane * DPL + j] = gb[j];
+        for (int j = 0; j < DPL; ++j) atomicAdd(sAcc + WP * ACS + lane * DPL + j, gb[j]);
         __syncthreads();
         for (int e = threadIdx.x; e < (WP + 1) * DT; e += blockDim.x) {
             const int w = e / DT, d = e % DT;
-            if (w < W || w == WP) {
-                double s = 0.0;
-                for (int q = 0; q < nw; ++q) s += (double)red[((size_t)q * (WP + 1) + w) * DT + d];
-                if (w == WP) prec[(size_t)DT * W + d] = s;
-                else prec[(size_t)d * W + w] = s;
-            }
+            if (w == WP) prec[(size_t)DT * W + d] = (double)sAcc[w * ACS + d];
+            else if (w < W) prec[(size_t)d * W + w] = (double)sAcc[w * ACS + d];
         }
     }
 };
@@ -494,10 +500,13 @@ k_lin_bwd_mma(const float* __restrict__ gout, const float* __restrict__ A, const
     const long long warp = (long long)blockIdx.x * nw + wid;
     const long long nwarps = (long long)gridDim.x * nw;
     uint2* sW = reinterpret_cast<uint2*>(dyn_smem);
-    float* sG = reinterpret_cast<float*>(dyn_smem + M::W_BYTES) + (size_t)wid * (TR * GS + TR * AS);
+    float* sAcc = reinterpret_cast<float*>(dyn_smem + M::W_BYTES);
+    float* sG = reinterpret_cast<float*>(dyn_smem + M::W_BYTES + M::ACC_BYTES) + (size_t)wid * (TR * GS + TR * AS);
     float* sa = sG + TR * GS;
     M::fill_w(sW, Wl, W);
+    M::zero_acc(sAcc);
     __syncthreads();
+    int since_flush = 0;
     float acc2[M::NT2][4], gb[DPL];
 #pragma unroll
     for (int nt = 0; nt < M::NT2; ++nt) acc2[nt][0] = acc2[nt][1] = acc2[nt][2] = acc2[nt][3] = 0.f;
@@ -551,9 +560,14 @@ k_lin_bwd_mma(const float* __restrict__ gout, const float* __restrict__ A, const
             }
         }
         M::gwl_acc(sG, sa, lane, acc2);
+        if (++since_flush == 4) {                                             // 24 chained MMAs per accumulator
+            M::flush(acc2, sAcc, lane);
+            since_flush = 0;
+        }
     }
+    if (since_flush) M::flush(acc2, sAcc, lane);
     __syncthreads();
-    M::reduce(acc2, gb, reinterpret_cast<float*>(dyn_smem), W, part + (size_t)blockIdx.x * ((size_t)D * W + D));
+    M::finish(gb, sAcc, W, part + (size_t)blockIdx.x * ((size_t)D * W + D));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1103,9 +1117,12 @@ k_bwd3_mma(HeadArgs h, BwdArgs g, double* __restrict__ part) {
     }
     constexpr size_t STAGE_FLOATS = (size_t)8 * (RowStage<WP>::WARP_FLOATS + XhStage<DPL>::WARP_FLOATS);
     uint2* sW = reinterpret_cast<uint2*>(reinterpret_cast<float*>(dyn_smem) + STAGE_FLOATS);
-    float* sG = reinterpret_cast<float*>(dyn_smem + STAGE_FLOATS * sizeof(float) + M::W_BYTES) + (size_t)wid * TR * GS;
+    float* sAcc = reinterpret_cast<float*>(dyn_smem + STAGE_FLOATS * sizeof(float) + M::W_BYTES);
+    float* sG = reinterpret_cast<float*>(dyn_smem + STAGE_FLOATS * sizeof(float) + M::W_BYTES + M::ACC_BYTES) + (size_t)wid * TR * GS;
     M::fill_w(sW, h.Wl, h.W);
+    M::zero_acc(sAcc);
     __syncthreads();
+    int since_flush = 0;
     float acc2[M::NT2][4], gb[DPL];
 #pragma unroll
     for (int nt = 0; nt < M::NT2; ++nt) acc2[nt][0] = acc2[nt][1] = acc2[nt][2] = acc2[nt][3] = 0.f;
@@ -1166,10 +1183,15 @@ k_bwd3_mma(HeadArgs h, BwdArgs g, double* __restrict__ part) {
             }
             M::gwl_acc(sG, sa_, lane, acc2);
             __syncwarp();
+            if (++since_flush == 4) {                                             // 24 chained MMAs per accumulator
+                M::flush(acc2, sAcc, lane);
+                since_flush = 0;
+            }
         GDN_BATCH_LOOP_END
     GDN_TASK_LOOP_END
+    if (since_flush) M::flush(acc2, sAcc, lane);
     __syncthreads();
-    M::reduce(acc2, gb, reinterpret_cast<float*>(dyn_smem), h.W, part + (size_t)blockIdx.x * ((size_t)h.D * h.W + h.D));
+    M::finish(gb, sAcc, h.W, part + (size_t)blockIdx.x * ((size_t)h.D * h.W + h.D));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1420,6 +1442,13 @@ static size_t dw_smem2(bool need_a, bool buf, int nv_double, bool red33) {
         KERNEL<<<GRID, 256, sm__, ST>>>(__VA_ARGS__);                                                  \
     } while (0)
 
+// GDN_NO_MMA (bit mask, diagnostics): 1 = k_lin_bwd, 2 = k_bwd3 fall back to the FMA kernels
+static int no_mma() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GDN_NO_MMA"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 static int dw_grid(long long tasks) {
     long long g = (tasks + 7) / 8;
     const int cap = 4 * num_sms();      // ws partial-record regions are sized for this many CTAs
@@ -1443,8 +1472,7 @@ static int launch_lin_bwd_mma(const Shape& s, const float* gout, const float* A,
                               double* part, int* nrec, cudaStream_t st) {
     using M = LinBwdMma<DPL, WP>;
     constexpr int TR = M::TR, nw = 8;
-    const size_t tiles = M::W_BYTES + (size_t)nw * (M::G_BYTES + (size_t)TR * M::AS * 4);
-    const size_t smem = tiles > M::RED_BYTES ? tiles : M::RED_BYTES;
+    const size_t smem = M::W_BYTES + M::ACC_BYTES + (size_t)nw * (M::G_BYTES + (size_t)TR * M::AS * 4);
     long long g = (s.n + (long long)TR * nw - 1) / ((long long)TR * nw);
     if (g > 2 * num_sms()) g = 2 * num_sms();
     const int grid = (int)(g < 1 ? 1 : g);
@@ -1459,7 +1487,8 @@ static int launch_lin_bwd_mma(const Shape& s, const float* gout, const float* A,
 int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_layer_params* p, float* gA,
                    double* part, int* nrec, cudaStream_t st) {
     // tensor-core path for the shapes it is built for
-    if (s.DPL == 4 && s.WP == 16) return launch_lin_bwd_mma<4, 16>(s, gout, A, p, gA, part, nrec, st);
+    if (no_mma() & 1) {}
+    else if (s.DPL == 4 && s.WP == 16) return launch_lin_bwd_mma<4, 16>(s, gout, A, p, gA, part, nrec, st);
     if (s.DPL == 4 && s.WP == 8) return launch_lin_bwd_mma<4, 8>(s, gout, A, p, gA, part, nrec, st);
     if (s.DPL == 2 && s.WP == 16) return launch_lin_bwd_mma<2, 16>(s, gout, A, p, gA, part, nrec, st);
     if (s.DPL == 2 && s.WP == 8) return launch_lin_bwd_mma<2, 8>(s, gout, A, p, gA, part, nrec, st);
@@ -1595,8 +1624,7 @@ template <int DPL, int WP>
 static int launch_bwd3_mma(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st) {
     using M = LinBwdMma<DPL, WP>;
     const size_t stage = (size_t)8 * (RowStage<WP>::WARP_FLOATS + XhStage<DPL>::WARP_FLOATS) * sizeof(float);
-    const size_t tiles = stage + M::W_BYTES + 8 * M::G_BYTES;
-    const size_t smem = tiles > M::RED_BYTES ? tiles : M::RED_BYTES;
+    const size_t smem = stage + M::W_BYTES + M::ACC_BYTES + 8 * M::G_BYTES;
     // one resident CTA per SM (shared-memory bound): a persistent grid, each CTA walks its share of the tasks
     int grid = dw_grid((long long)s.N * s.S);
     const int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -1611,7 +1639,8 @@ static int launch_bwd3_mma(const Shape& s, const HeadArgs& h, const BwdArgs& g, 
 int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
     const bool buf = h.xh1 != nullptr;
-    if (buf && s.DPL == 4 && s.WP == 16) return launch_bwd3_mma<4, 16>(s, h, g, part, nrec, st);
+    if (no_mma() & 2) {}
+    else if (buf && s.DPL == 4 && s.WP == 16) return launch_bwd3_mma<4, 16>(s, h, g, part, nrec, st);
     if (buf && s.DPL == 4 && s.WP == 8) return launch_bwd3_mma<4, 8>(s, h, g, part, nrec, st);
     if (buf && s.DPL == 2 && s.WP == 16) return launch_bwd3_mma<2, 16>(s, h, g, part, nrec, st);
     if (buf && s.DPL == 2 && s.WP == 8) return launch_bwd3_mma<2, 8>(s, h, g, part, nrec, st);
