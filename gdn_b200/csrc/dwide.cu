@@ -755,34 +755,26 @@ k_fwd_stats2(HeadArgs h, double* __restrict__ part) {
 // channel l*DPL + j.  Explicit mask (tests): bit = mask != 0.  Otherwise Philox4x32-10: one call
 // yields eight 16-bit uniforms, keep iff u16 >= round(p * 65536); counter = (row*DPL + j)*4 + q.
 template <int DPL>
-__device__ __forceinline__ void gen_keep_words(const HeadArgs& h, size_t r, uint32_t (&words)[DPL]) {
+__device__ __forceinline__ uint32_t gen_keep_word(const HeadArgs& h, size_t r, int j) {
+    uint32_t w = 0u;
     if (h.mask != nullptr) {
         const float* m = h.mask + r * h.D;
-#pragma unroll
-        for (int j = 0; j < DPL; ++j) {
-            uint32_t w = 0u;
-            for (int l = 0; l < 32; ++l) w |= (m[l * DPL + j] != 0.f) ? (1u << l) : 0u;
-            words[j] = w;
-        }
+        for (int l = 0; l < 32; ++l) w |= (m[l * DPL + j] != 0.f) ? (1u << l) : 0u;
     } else {
         const uint32_t thr16 = (uint32_t)(h.p_drop * 65536.f + 0.5f);
         const unsigned long long offset = h.offset + (h.offset_dev ? *h.offset_dev : 0ull);
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) {
-            uint32_t w = 0u;
+        for (int q = 0; q < 4; ++q) {
+            const uint4 rnd = philox4x32_10((unsigned long long)(r * DPL + j) * 4ull + q, offset, h.seed);
+            const uint32_t x[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint4 rnd = philox4x32_10((unsigned long long)(r * DPL + j) * 4ull + q, offset, h.seed);
-                const uint32_t x[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    w |= ((x[c] & 0xffffu) >= thr16 ? 1u : 0u) << (q * 8 + c * 2);
-                    w |= ((x[c] >> 16) >= thr16 ? 1u : 0u) << (q * 8 + c * 2 + 1);
-                }
+            for (int c = 0; c < 4; ++c) {
+                w |= ((x[c] & 0xffffu) >= thr16 ? 1u : 0u) << (q * 8 + c * 2);
+                w |= ((x[c] >> 16) >= thr16 ? 1u : 0u) << (q * 8 + c * 2 + 1);
             }
-            words[j] = w;
         }
     }
+    return w;
 }
 
 // pred[b,i] = sum_d hm[d] wo[d] + bo;  training: dropout + keep bits saved
@@ -808,10 +800,19 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
         load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
         GDN_BATCH_LOOP_BEGIN(h)
             float my_pred = 0.f;
-            uint32_t my_bits[DPL];
+            // keep words of the batch: in the buffered passes a batch is 16 rows, so two lanes share a row
+            // (lane l: row l & 15, words [(l >> 4) * H, +H)) and all 32 lanes run the generator
+            constexpr bool SPLIT = BUF_ && DPL >= 2;
+            constexpr int H = SPLIT ? DPL / 2 : DPL;
+            const int brow = SPLIT ? (lane & 15) : lane, bhalf = SPLIT ? (lane >> 4) : 0;
+            uint32_t my_bits[H];
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) my_bits[j] = 0xffffffffu;
-            if (drop && lane < nb) gen_keep_words<DPL>(h, (size_t)(b0 + lane) * h.N + i, my_bits);
+            for (int jj = 0; jj < H; ++jj) my_bits[jj] = 0xffffffffu;
+            if (drop && brow < nb) {
+#pragma unroll
+                for (int jj = 0; jj < H; ++jj)
+                    my_bits[jj] = gen_keep_word<DPL>(h, (size_t)(b0 + brow) * h.N + i, bhalf * H + jj);
+            }
 #pragma unroll 2
             for (int rr = 0; rr < nb; ++rr) {
                 float a[WP], xh1[DPL], y1[DPL];
@@ -819,7 +820,7 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
                 float dot = 0.f;
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) {
-                    const uint32_t word = __shfl_sync(0xffffffffu, my_bits[j], rr);
+                    const uint32_t word = __shfl_sync(0xffffffffu, my_bits[j % H], SPLIT ? rr + 16 * (j / H) : rr);
                     const float kf = drop ? (((word >> lane) & 1u) ? h.scale : 0.f) : 1.f;
                     const float p = fmaxf(y1[j], 0.f) * v[j];
                     const float y2 = fmaf(g2[j], fmaf(p, k2a[j], k2b[j]), be2[j]);
@@ -828,13 +829,11 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
                 dot = warp_sum(dot);
                 if (lane == rr) my_pred = dot + bo;
             }
-            if (lane < nb) {
-                const size_t r = (size_t)(b0 + lane) * h.N + i;
-                pred[r] = my_pred;
-                if (drop) {
+            if (lane < nb) pred[(size_t)(b0 + lane) * h.N + i] = my_pred;
+            if (drop && brow < nb) {
+                const size_t r = (size_t)(b0 + brow) * h.N + i;
 #pragma unroll
-                    for (int j = 0; j < DPL; ++j) h.bits[r * DPL + j] = my_bits[j];
-                }
+                for (int jj = 0; jj < H; ++jj) h.bits[r * DPL + bhalf * H + jj] = my_bits[jj];
             }
         GDN_BATCH_LOOP_END
     GDN_TASK_LOOP_END
@@ -1196,28 +1195,29 @@ k_bwd3_mma(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 
 // ---------------------------------------------------------------------------------------
 // per-CTA partial records -> one record of doubles (fixed summation order: deterministic)
-// block (32, 8): x <-> entry, y strides the records; grid = ceil(rec / 32)
+// block (32, 32): x <-> entry, y strides the records; grid = ceil(rec / 32)
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_reduce_part(const T* __restrict__ part, int nrec, int rec, double* __restrict__ sums) {
-    __shared__ double sh[8][33];
+__global__ void __launch_bounds__(1024)
+k_reduce_part(const T* __restrict__ part, int nrec, int rec, double* __restrict__ sums) {
+    __shared__ double sh[32][33];
     const int e = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0;
     if (e < rec)
-        for (int q = threadIdx.y; q < nrec; q += 8) s += (double)part[(size_t)q * rec + e];
+        for (int q = threadIdx.y; q < nrec; q += 32) s += (double)part[(size_t)q * rec + e];
     sh[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && e < rec) {
         double t = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x];
+        for (int k = 0; k < 32; ++k) t += sh[k][threadIdx.x];
         sums[e] = t;
     }
 }
 
 template <typename T>
 static int reduce_part(const T* part, int nrec, int rec, double* sums, cudaStream_t st) {
-    k_reduce_part<T><<<(rec + 31) / 32, dim3(32, 8), 0, st>>>(part, nrec, rec, sums);
+    k_reduce_part<T><<<(rec + 31) / 32, dim3(32, 32), 0, st>>>(part, nrec, rec, sums);
     GDN_CHECK_LAUNCH("k_reduce_part");
     return 0;
 }
