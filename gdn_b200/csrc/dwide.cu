@@ -1088,36 +1088,33 @@ k_bwd3(HeadArgs h, BwdArgs g, double* __restrict__ part) {
     }
 }
 
-// pass 3, tensor-core version (saved xh1, D in {64, 128}, W <= 16): per batch of 16 windows the warp
-// first walks the rows lane <-> channels (the BatchNorm/ReLU chain down to g_z, g_bias partials) and parks
-// g_z [16 x D] in shared memory, then runs the two contractions of LinBwdMma on that tile.
-// dynamic smem: per warp A tile + xh1 tile (as the other passes) | Wl {hi,lo} | per warp g_z tile [16][D+4]
+// pass 3, tensor-core version (saved xh1, D in {64, 128}, W <= 16).  Per batch of 16 windows of one sensor
+// the warp walks the rows lane <-> channels (the BatchNorm/ReLU chain down to g_z, g_bias partials),
+// overwriting the staged xh1 tile with g_z IN PLACE, then runs the two contractions of LinBwdMma on that tile.
+// The next batch's xh1 and A rows are already in flight (cp.async, two buffers per warp) while the current
+// one is computed, and its g_pred / keep words wait in registers: no exposed global latency in the loop.
+// dynamic smem: Wl {hi,lo} | accumulator image | per warp 2 x (xh1/g_z tile [16][D+4], A tile [16][WP+4])
 template <int DPL, int WP>
 __global__ void __launch_bounds__(256)
 k_bwd3_mma(HeadArgs h, BwdArgs g, double* __restrict__ part) {
-    constexpr bool NEED_A_ = true, BUF_ = true;
     using M = LinBwdMma<DPL, WP>;
-    static_assert(M::TR == XH_ROWS, "tile rows = rows per buffered batch");
     constexpr int GS = M::GS, AS = M::AS, TR = M::TR;
+    constexpr int BUF_FLOATS = TR * GS + TR * AS;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     RowEval<DPL, WP> re;
     BwdRow<DPL, WP> br;
-    re.init(h, threadIdx.x & 31, false);
-    br.init(h, threadIdx.x & 31);
-    const int wid = threadIdx.x >> 5;
+    re.init(h, lane, false);
+    br.init(h, lane);
     float cB2[DPL], cG2[DPL], s2c[DPL], cB1[DPL], cG1[DPL], s1c[DPL];
-    {
-        const int ln = threadIdx.x & 31;
-        load_chan<DPL>(g.c2, ln, cB2);
-        load_chan<DPL>(g.c2 + h.D, ln, cG2);
-        load_chan<DPL>(g.c1, ln, cB1);
-        load_chan<DPL>(g.c1 + h.D, ln, cG1);
+    load_chan<DPL>(g.c2, lane, cB2);
+    load_chan<DPL>(g.c2 + h.D, lane, cG2);
+    load_chan<DPL>(g.c1, lane, cB1);
+    load_chan<DPL>(g.c1 + h.D, lane, cG1);
 #pragma unroll
-        for (int j = 0; j < DPL; ++j) { s2c[j] = br.g2[j] * br.k2a[j]; s1c[j] = re.g1[j] * re.k1a[j]; }
-    }
-    constexpr size_t STAGE_FLOATS = (size_t)8 * (RowStage<WP>::WARP_FLOATS + XhStage<DPL>::WARP_FLOATS);
-    uint2* sW = reinterpret_cast<uint2*>(reinterpret_cast<float*>(dyn_smem) + STAGE_FLOATS);
-    float* sAcc = reinterpret_cast<float*>(dyn_smem + STAGE_FLOATS * sizeof(float) + M::W_BYTES);
-    float* sG = reinterpret_cast<float*>(dyn_smem + STAGE_FLOATS * sizeof(float) + M::W_BYTES + M::ACC_BYTES) + (size_t)wid * TR * GS;
+    for (int j = 0; j < DPL; ++j) { s2c[j] = br.g2[j] * br.k2a[j]; s1c[j] = re.g1[j] * re.k1a[j]; }
+    uint2* sW = reinterpret_cast<uint2*>(dyn_smem);
+    float* sAcc = reinterpret_cast<float*>(dyn_smem + M::W_BYTES);
+    float* sbuf = reinterpret_cast<float*>(dyn_smem + M::W_BYTES + M::ACC_BYTES) + (size_t)wid * 2 * BUF_FLOATS;
     M::fill_w(sW, h.Wl, h.W);
     M::zero_acc(sAcc);
     __syncthreads();
@@ -1127,67 +1124,144 @@ k_bwd3_mma(HeadArgs h, BwdArgs g, double* __restrict__ part) {
     for (int nt = 0; nt < M::NT2; ++nt) acc2[nt][0] = acc2[nt][1] = acc2[nt][2] = acc2[nt][3] = 0.f;
 #pragma unroll
     for (int j = 0; j < DPL; ++j) gb[j] = 0.f;
-    GDN_TASK_LOOP_BEGIN(h)
-        float v[DPL];
-        load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
-        GDN_BATCH_LOOP_BEGIN(h)
-            BwdSide<DPL> side;
-            side.load(h, g.gpred, i, b0, nb, lane);
-#pragma unroll 2
-            for (int rr = 0; rr < nb; ++rr) {
-                float a[WP], xh1[DPL], y1[DPL], kf[DPL], gz[DPL];
-                row_inputs<DPL, WP, false, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
-                const float gp = side.row(h, rr, lane, kf);
+
+    const long long warp_ = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps_ = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long tasks_ = (long long)h.N * h.S;
+    // work items of this warp: (task, b0) in task-major order; task -> (sensor i, window range [b_lo, b_hi))
+    auto task_range = [&](long long task, int& i, int& b_lo, int& b_hi) {
+        i = (int)(task / h.S);
+        const int sp = (int)(task % h.S);
+        b_lo = sp * h.rps;
+        b_hi = min(h.B, b_lo + h.rps);
+    };
+    // stage the xh1 rows and the A rows of batch (i, b0, nb) into buffer `buf` (asynchronous)
+    auto issue = [&](int i, int b0, int nb, float* buf) {
+        float* sx = buf;
+        float* sa = buf + TR * GS;
+        const float* xsrc = h.xh1 + ((size_t)b0 * h.N + i) * h.D + lane * DPL;
+        const uint32_t xdst = (uint32_t)__cvta_generic_to_shared(sx + lane * DPL);
+        for (int rr = 0; rr < nb; ++rr) {
+            const float* src = xsrc + (size_t)rr * h.N * h.D;
+            const uint32_t dst = xdst + rr * GS * 4;
+            if (DPL == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        }
+        if (lane < nb) {
+            const float* arow = h.A + ((size_t)(b0 + lane) * h.N + i) * h.W;
+            const uint32_t adst = (uint32_t)__cvta_generic_to_shared(sa + lane * AS);
+            if ((h.W & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < DPL; ++j) {
-                    const float p = fmaxf(y1[j], 0.f) * v[j];
-                    const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
-                    const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
-                    const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
-                    const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);
-                    const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
-                    gz[j] = s1c[j] * (gy1 - cB1[j] - xh1[j] * cG1[j]);            // d loss / d z
-                    gb[j] += gz[j];
+                for (int w = 0; w < WP; w += 4) {
+                    const int nbytes = w < h.W ? 16 : 0;                           // zero fill beyond W
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(adst + w * 4), "l"(arow + (w < h.W ? w : 0)),
+                                 "r"(nbytes) : "memory");
                 }
-                store_chan<DPL>(sG + rr * GS, lane, gz);
+            } else {
+#pragma unroll
+                for (int w = 0; w < WP; ++w) {
+                    const int nbytes = w < h.W ? 4 : 0;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(adst + w * 4), "l"(arow + (w < h.W ? w : 0)),
+                                 "r"(nbytes) : "memory");
+                }
             }
-            if (nb < TR) {                                                        // tail: zero rows for the MMAs
-                float z[DPL];
+        }
+    };
+
+    long long task = warp_;
+    int i = 0, b_lo = 0, b_hi = 0, b0 = 0;
+    bool have = task < tasks_;
+    BwdSide<DPL> side;
+    if (have) {
+        task_range(task, i, b_lo, b_hi);
+        b0 = b_lo;
+        issue(i, b0, min(TR, b_hi - b0), sbuf);
+        side.load(h, g.gpred, i, b0, min(TR, b_hi - b0), lane);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    float v[DPL];
+    bool new_task = true;
+    for (int k = 0; have; ++k) {
+        const int nb = min(TR, b_hi - b0);
+        // the batch after this one
+        long long ntask = task;
+        int ni = i, nb_lo = b_lo, nb_hi = b_hi, nb0 = b0 + TR;
+        bool nhave = true;
+        if (nb0 >= b_hi) {
+            ntask = task + nwarps_;
+            nhave = ntask < tasks_;
+            if (nhave) { task_range(ntask, ni, nb_lo, nb_hi); nb0 = nb_lo; }
+        }
+        BwdSide<DPL> nside = side;
+        __syncwarp();                                         // everyone is done with the buffer about to be refilled
+        if (nhave) {
+            issue(ni, nb0, min(TR, nb_hi - nb0), sbuf + ((k + 1) & 1) * BUF_FLOATS);
+            nside.load(h, g.gpred, ni, nb0, min(TR, nb_hi - nb0), lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory"); // this batch's copies have landed
+        __syncwarp();
+        float* sG = sbuf + (k & 1) * BUF_FLOATS;
+        float* sa = sG + TR * GS;
+        if (new_task) load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
+#pragma unroll 2
+        for (int rr = 0; rr < nb; ++rr) {
+            float xh1[DPL], y1[DPL], kf[DPL], gz[DPL];
+            load_chan_vec<DPL>(sG + rr * GS, lane, xh1);
+            re.from_saved(xh1, y1);
+            const float gp = side.row(h, rr, lane, kf);
 #pragma unroll
-                for (int j = 0; j < DPL; ++j) z[j] = 0.f;
-                for (int rr = nb; rr < TR; ++rr) store_chan<DPL>(sG + rr * GS, lane, z);
-                for (int e = lane; e < (TR - nb) * AS; e += 32) sa_[nb * AS + e] = 0.f;
+            for (int j = 0; j < DPL; ++j) {
+                const float p = fmaxf(y1[j], 0.f) * v[j];
+                const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
+                const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
+                const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
+                const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);
+                const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
+                gz[j] = s1c[j] * (gy1 - cB1[j] - xh1[j] * cG1[j]);            // d loss / d z
+                gb[j] += gz[j];
             }
-            __syncwarp();
-            float c1[M::NT1][4];
-            M::ga_tile(sG, sW, lane, c1);
-            {
-                const int gg = lane >> 2, t = lane & 3;
+            store_chan<DPL>(sG + rr * GS, lane, gz);                            // in place
+        }
+        if (nb < TR) {                                                        // tail: zero rows for the MMAs
+            float z[DPL];
 #pragma unroll
-                for (int nt = 0; nt < M::NT1; ++nt) {
-                    const int w0 = 8 * nt + 2 * t;
+            for (int j = 0; j < DPL; ++j) z[j] = 0.f;
+            for (int rr = nb; rr < TR; ++rr) store_chan<DPL>(sG + rr * GS, lane, z);
+            for (int e = lane; e < (TR - nb) * AS; e += 32) sa[nb * AS + e] = 0.f;
+        }
+        __syncwarp();
+        float c1[M::NT1][4];
+        M::ga_tile(sG, sW, lane, c1);
+        {
+            const int gg = lane >> 2, t = lane & 3;
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int rr = gg + 8 * hh;
-                        if (rr < nb && w0 < h.W) {
-                            float* o = g.gA + ((size_t)(b0 + rr) * h.N + i) * h.W + w0;
-                            if ((h.W & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(c1[nt][2 * hh], c1[nt][2 * hh + 1]);
-                            else {
-                                o[0] = c1[nt][2 * hh];
-                                if (w0 + 1 < h.W) o[1] = c1[nt][2 * hh + 1];
-                            }
+            for (int nt = 0; nt < M::NT1; ++nt) {
+                const int w0 = 8 * nt + 2 * t;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int rr = gg + 8 * hh;
+                    if (rr < nb && w0 < h.W) {
+                        float* o = g.gA + ((size_t)(b0 + rr) * h.N + i) * h.W + w0;
+                        if ((h.W & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(c1[nt][2 * hh], c1[nt][2 * hh + 1]);
+                        else {
+                            o[0] = c1[nt][2 * hh];
+                            if (w0 + 1 < h.W) o[1] = c1[nt][2 * hh + 1];
                         }
                     }
                 }
             }
-            M::gwl_acc(sG, sa_, lane, acc2);
-            __syncwarp();
-            if (++since_flush == 4) {                                             // 24 chained MMAs per accumulator
-                M::flush(acc2, sAcc, lane);
-                since_flush = 0;
-            }
-        GDN_BATCH_LOOP_END
-    GDN_TASK_LOOP_END
+        }
+        M::gwl_acc(sG, sa, lane, acc2);
+        if (++since_flush == 4) {                                             // 24 chained MMAs per accumulator
+            M::flush(acc2, sAcc, lane);
+            since_flush = 0;
+        }
+        new_task = ntask != task;
+        task = ntask; i = ni; b_lo = nb_lo; b_hi = nb_hi; b0 = nb0; have = nhave;
+        side = nside;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (since_flush) M::flush(acc2, sAcc, lane);
     __syncthreads();
     M::finish(gb, sAcc, h.W, part + (size_t)blockIdx.x * ((size_t)h.D * h.W + h.D));
@@ -1623,8 +1697,7 @@ int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
 template <int DPL, int WP>
 static int launch_bwd3_mma(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st) {
     using M = LinBwdMma<DPL, WP>;
-    const size_t stage = (size_t)8 * (RowStage<WP>::WARP_FLOATS + XhStage<DPL>::WARP_FLOATS) * sizeof(float);
-    const size_t smem = stage + M::W_BYTES + M::ACC_BYTES + 8 * M::G_BYTES;
+    const size_t smem = M::W_BYTES + M::ACC_BYTES + (size_t)8 * 2 * (M::G_BYTES + (size_t)M::TR * M::AS * sizeof(float));
     // one resident CTA per SM (shared-memory bound): a persistent grid, each CTA walks its share of the tasks
     int grid = dw_grid((long long)s.N * s.S);
     const int per_sm = (int)((227 * 1024) / (smem + 1024));
