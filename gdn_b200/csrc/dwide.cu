@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "launchers.h"
 #include "mma_tf32.cuh"
+#include "f32x2.cuh"
 
 namespace gdn {
 
@@ -178,12 +179,18 @@ struct RowStage {
 // Per-lane prefetch buffer for the saved BatchNorm-1 input xh1[r, :] (training path): lane l copies
 // its own DPL channels of up to 32 rows into shared memory with cp.async (all copies in flight at once,
 // no registers held), then reads them back itself -- no cross-lane traffic, no barrier beyond the wait.
-constexpr int XH_ROWS = 16;      // rows per batch of the buffered passes (8 KB per warp at D = 128: 3 CTAs per SM)
+constexpr int XH_ROWS = 8;       // rows per batch of the buffered passes; two buffers per warp (8 KB at D = 128)
 template <int DPL>
 struct XhStage {
-    static constexpr int WARP_FLOATS = XH_ROWS * DPL * 32;
-    __device__ __forceinline__ static void fill(float* sx, const float* __restrict__ first, size_t row_stride,
-                                                int nb, int lane) {
+    static constexpr int BUF_FLOATS = XH_ROWS * DPL * 32;            // one buffer
+    static constexpr int SIDE_FLOATS = XH_ROWS * (1 + DPL);          // g_pred + keep words of the batch's rows
+    static constexpr int WARP_FLOATS = 2 * (BUF_FLOATS + SIDE_FLOATS);
+    __device__ __forceinline__ static float* buf(float* sx, int k) { return sx + (k & 1) * (BUF_FLOATS + SIDE_FLOATS); }
+    // asynchronous copy of nb rows of xh1 (row stride row_stride floats) and, if gpred != nullptr, of the
+    // rows' g_pred and dropout keep words (r0 = flat row index of the first row, rows N apart); one group
+    __device__ __forceinline__ static void fill(float* sx, const float* __restrict__ first, size_t row_stride, int nb,
+                                                int lane, const float* __restrict__ gpred, const uint32_t* __restrict__ bits,
+                                                size_t r0, size_t rstep) {
         for (int rr = 0; rr < nb; ++rr) {
             const float* src = first + (size_t)rr * row_stride + lane * DPL;
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sx + (rr * 32 + lane) * DPL);
@@ -198,9 +205,22 @@ struct XhStage {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
             }
         }
+        if (gpred != nullptr && lane < nb) {
+            float* side = sx + BUF_FLOATS;
+            const size_t r = r0 + (size_t)lane * rstep;
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(side + lane);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0), "l"(gpred + r) : "memory");
+            if (bits != nullptr) {
+                const uint32_t d1 = (uint32_t)__cvta_generic_to_shared(side + XH_ROWS + lane * DPL);
+#pragma unroll
+                for (int j = 0; j < DPL; ++j)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d1 + 4 * j), "l"(bits + r * DPL + j) : "memory");
+            }
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    __device__ __forceinline__ static void wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+    __device__ __forceinline__ static void commit_empty() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    __device__ __forceinline__ static void wait_current() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
     __device__ __forceinline__ static void get(const float* sx, int rr, int lane, float (&v)[DPL]) {
         load_chan_vec<DPL>(sx + rr * 32 * DPL, lane, v);
     }
@@ -697,26 +717,56 @@ __device__ __forceinline__ void row_inputs(const RowEval<DPL, WP>& re, const flo
     const size_t rstride_ = (size_t)(h).N * (h).W;                                               \
     constexpr int WARP_SMEM_ = (NEED_A_ ? RowStage<WP>::WARP_FLOATS : 0) + (BUF_ ? XhStage<DPL>::WARP_FLOATS : 0); \
     float* sa_ = reinterpret_cast<float*>(dyn_smem) + (size_t)(threadIdx.x >> 5) * WARP_SMEM_;   \
-    float* sx_ = sa_ + (NEED_A_ ? RowStage<WP>::WARP_FLOATS : 0);                                \
+    float* sxbase_ = sa_ + (NEED_A_ ? RowStage<WP>::WARP_FLOATS : 0);                            \
+    int pk_ = 0;             /* buffered passes: batch counter (buffer parity) */                \
+    bool pf_ = false;        /* ... and whether the coming batch is already in flight */         \
     for (long long task_ = warp_; task_ < tasks_; task_ += nwarps_) {                            \
         const int i = (int)(task_ / (h).S), sp = (int)(task_ % (h).S);                           \
         const int b_lo = sp * (h).rps, b_hi = min((h).B, b_lo + (h).rps);
 #define GDN_TASK_LOOP_END }
-// inside a task: batches of up to 32 windows of sensor i
-#define GDN_BATCH_LOOP_BEGIN(h)                                                                  \
+// inside a task: batches of up to 32 windows of sensor i (8 in the buffered passes, whose staging is
+// double-buffered: while a batch is processed the next one -- of this task or the warp's next task -- is
+// already in flight; gp_/bits_ = g_pred and keep-word arrays staged with it, or nullptr)
+#define GDN_BATCH_LOOP_BEGIN2(h, gp_, bits_)                                                     \
     for (int b0 = b_lo; b0 < b_hi; b0 += (BUF_ ? XH_ROWS : 32)) {                                \
         const int nb = min(BUF_ ? XH_ROWS : 32, b_hi - b0);                                      \
+        float* sx_ = sxbase_;                                                                    \
         if (BUF_) {                                                                              \
+            sx_ = XhStage<DPL>::buf(sxbase_, pk_);                                               \
+            const size_t xrow_ = (size_t)(h).N * (h).D;                                          \
+            if (!pf_) {                                                                          \
+                __syncwarp();                                                                    \
+                XhStage<DPL>::fill(sx_, (h).xh1 + ((size_t)b0 * (h).N + i) * (h).D, xrow_, nb, lane, gp_, bits_, \
+                                   (size_t)b0 * (h).N + i, (size_t)(h).N);                       \
+            }                                                                                    \
+            int ni_ = i, nb0_ = b0 + XH_ROWS, nhi_ = b_hi;                                       \
+            bool nh_ = true;                                                                     \
+            if (nb0_ >= b_hi) {                                                                  \
+                const long long t2_ = task_ + nwarps_;                                           \
+                nh_ = t2_ < tasks_;                                                              \
+                if (nh_) {                                                                       \
+                    ni_ = (int)(t2_ / (h).S);                                                    \
+                    nb0_ = (int)(t2_ % (h).S) * (h).rps;                                         \
+                    nhi_ = min((h).B, nb0_ + (h).rps);                                           \
+                }                                                                                \
+            }                                                                                    \
             __syncwarp();                                                                        \
-            XhStage<DPL>::fill(sx_, (h).xh1 + ((size_t)b0 * (h).N + i) * (h).D, (size_t)(h).N * (h).D, nb, lane); \
+            if (nh_) XhStage<DPL>::fill(XhStage<DPL>::buf(sxbase_, pk_ + 1), (h).xh1 + ((size_t)nb0_ * (h).N + ni_) * (h).D, \
+                                        xrow_, min(XH_ROWS, nhi_ - nb0_), lane, gp_, bits_,        \
+                                        (size_t)nb0_ * (h).N + ni_, (size_t)(h).N);              \
+            else XhStage<DPL>::commit_empty();                                                   \
+            pf_ = nh_;                                                                           \
+            ++pk_;                                                                               \
+            XhStage<DPL>::wait_current();                                                        \
+            __syncwarp();                                                                        \
         }                                                                                        \
-        if (NEED_A_) RowStage<WP>::fill(sa_, (h).A + ((size_t)b0 * (h).N + i) * (h).W, rstride_, nb, (h).W, lane); \
-        if (BUF_) XhStage<DPL>::wait();
+        if (NEED_A_) RowStage<WP>::fill(sa_, (h).A + ((size_t)b0 * (h).N + i) * (h).W, rstride_, nb, (h).W, lane);
+#define GDN_BATCH_LOOP_BEGIN(h) GDN_BATCH_LOOP_BEGIN2(h, ((const float*)nullptr), ((const uint32_t*)nullptr))
 #define GDN_BATCH_LOOP_END }
 
 // BN2 batch statistics: sum_r p, sum_r p^2 -> part record [2*D] doubles
 template <int DPL, int WP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (DPL <= 4 && DPL * WP <= 64) ? 2 : 1)
 k_fwd_stats2(HeadArgs h, double* __restrict__ part) {
     constexpr bool NEED_A_ = true, BUF_ = false;
     RowEval<DPL, WP> re;
@@ -800,18 +850,19 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
         load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
         GDN_BATCH_LOOP_BEGIN(h)
             float my_pred = 0.f;
-            // keep words of the batch: in the buffered passes a batch is 16 rows, so two lanes share a row
-            // (lane l: row l & 15, words [(l >> 4) * H, +H)) and all 32 lanes run the generator
-            constexpr bool SPLIT = BUF_ && DPL >= 2;
-            constexpr int H = SPLIT ? DPL / 2 : DPL;
-            const int brow = SPLIT ? (lane & 15) : lane, bhalf = SPLIT ? (lane >> 4) : 0;
+            // keep words of the batch: in the buffered passes a batch is XH_ROWS = 8 rows, so four lanes share a
+            // row (lane l: row l & 7, words [(l >> 3) * H, +H)) and all 32 lanes run the generator
+            constexpr bool SPLIT = BUF_;
+            constexpr int LPR = 32 / XH_ROWS;                        // lanes per row
+            constexpr int H = SPLIT ? (DPL + LPR - 1) / LPR : DPL;   // words per lane
+            const int brow = SPLIT ? (lane % XH_ROWS) : lane, bpart = SPLIT ? (lane / XH_ROWS) : 0;
             uint32_t my_bits[H];
 #pragma unroll
             for (int jj = 0; jj < H; ++jj) my_bits[jj] = 0xffffffffu;
             if (drop && brow < nb) {
 #pragma unroll
                 for (int jj = 0; jj < H; ++jj)
-                    my_bits[jj] = gen_keep_word<DPL>(h, (size_t)(b0 + brow) * h.N + i, bhalf * H + jj);
+                    if (bpart * H + jj < DPL) my_bits[jj] = gen_keep_word<DPL>(h, (size_t)(b0 + brow) * h.N + i, bpart * H + jj);
             }
 #pragma unroll 2
             for (int rr = 0; rr < nb; ++rr) {
@@ -820,7 +871,7 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
                 float dot = 0.f;
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) {
-                    const uint32_t word = __shfl_sync(0xffffffffu, my_bits[j % H], SPLIT ? rr + 16 * (j / H) : rr);
+                    const uint32_t word = __shfl_sync(0xffffffffu, my_bits[j % H], SPLIT ? rr + XH_ROWS * (j / H) : rr);
                     const float kf = drop ? (((word >> lane) & 1u) ? h.scale : 0.f) : 1.f;
                     const float p = fmaxf(y1[j], 0.f) * v[j];
                     const float y2 = fmaf(g2[j], fmaf(p, k2a[j], k2b[j]), be2[j]);
@@ -833,7 +884,8 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
             if (drop && brow < nb) {
                 const size_t r = (size_t)(b0 + brow) * h.N + i;
 #pragma unroll
-                for (int jj = 0; jj < H; ++jj) h.bits[r * DPL + bhalf * H + jj] = my_bits[jj];
+                for (int jj = 0; jj < H; ++jj)
+                    if (bpart * H + jj < DPL) h.bits[r * DPL + bpart * H + jj] = my_bits[jj];
             }
         GDN_BATCH_LOOP_END
     GDN_TASK_LOOP_END
@@ -872,6 +924,15 @@ struct BwdSide {
             }
         }
     }
+    // same, from the side area the batch staging filled (buffered passes)
+    __device__ __forceinline__ void from_stage(const HeadArgs& h, const float* sx, int nb, int lane) {
+        const bool drop = h.training && h.p_drop > 0.f;
+        const float* side = sx + XhStage<DPL>::BUF_FLOATS;
+        gp = lane < nb ? side[lane] : 0.f;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+            bits[j] = (drop && lane < nb) ? __float_as_uint(side[XH_ROWS + lane * DPL + j]) : 0xffffffffu;
+    }
     // keep factor (0 or scale) of this lane's channels for row rr of the batch, and that row's g_pred
     __device__ __forceinline__ float row(const HeadArgs& h, int rr, int lane, float (&kf)[DPL]) const {
         const bool drop = h.training && h.p_drop > 0.f;
@@ -903,9 +964,10 @@ k_bwd1(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 #pragma unroll
         for (int j = 0; j < DPL; ++j) t0[j] = t1[j] = t2[j] = 0.f;
         float tb = 0.f;
-        GDN_BATCH_LOOP_BEGIN(h)
+        GDN_BATCH_LOOP_BEGIN2(h, g.gpred, ((h.training && h.p_drop > 0.f) ? (const uint32_t*)h.bits : (const uint32_t*)nullptr))
             BwdSide<DPL> side;
-            side.load(h, g.gpred, i, b0, nb, lane);
+            if (BUF_) side.from_stage(h, sx_, nb, lane);
+            else side.load(h, g.gpred, i, b0, nb, lane);
 #pragma unroll 2
             for (int rr = 0; rr < nb; ++rr) {
                 float a[WP], xh1[DPL], y1[DPL], kf[DPL];
@@ -962,6 +1024,9 @@ k_bwd2(HeadArgs h, BwdArgs g, double* __restrict__ part) {
 #pragma unroll
         for (int j = 0; j < DPL; ++j) s2c[j] = br.g2[j] * br.k2a[j];
     }
+    float ncB2[DPL], ncG2[DPL], wok[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) { ncB2[j] = -cB2[j]; ncG2[j] = -cG2[j]; wok[j] = br.wo[j]; }
     double acc[2 * DPL];
 #pragma unroll
     for (int q = 0; q < 2 * DPL; ++q) acc[q] = 0.0;
@@ -970,27 +1035,32 @@ k_bwd2(HeadArgs h, BwdArgs g, double* __restrict__ part) {
         load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
 #pragma unroll
         for (int j = 0; j < DPL; ++j) gv[j] = t1[j] = t2[j] = 0.f;
-        GDN_BATCH_LOOP_BEGIN(h)
+        GDN_BATCH_LOOP_BEGIN2(h, g.gpred, ((h.training && h.p_drop > 0.f) ? (const uint32_t*)h.bits : (const uint32_t*)nullptr))
             BwdSide<DPL> side;
-            side.load(h, g.gpred, i, b0, nb, lane);
+            if (BUF_) side.from_stage(h, sx_, nb, lane);
+            else side.load(h, g.gpred, i, b0, nb, lane);
 #pragma unroll 2
             for (int rr = 0; rr < nb; ++rr) {
                 float a[WP], xh1[DPL], y1[DPL], kf[DPL];
                 row_inputs<DPL, WP, NEED_A_, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
                 const float gp = side.row(h, rr, lane, kf);
-#pragma unroll
-                for (int j = 0; j < DPL; ++j) {
-                    const float r1 = fmaxf(y1[j], 0.f);
-                    const float p = r1 * v[j];
-                    const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
-                    const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
-                    const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
-                    const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);     // d loss / d p
-                    gv[j] = fmaf(gpp, r1, gv[j]);
-                    const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
-                    t1[j] = fmaf(gy1, xh1[j], t1[j]);                             // g_gamma1
-                    t2[j] += gy1;                                                 // g_beta1
-                }
+                // packed chain (pairs of channels per instruction)
+                float r1[DPL], p[DPL], xh2[DPL], y2[DPL], t[DPL], gy2[DPL], gpp[DPL], gy1[DPL];
+                vrelu<DPL>(r1, y1);
+                vmul<DPL>(p, r1, v);
+                vfma<DPL>(xh2, p, br.k2a, br.k2b);
+                vfma<DPL>(y2, br.g2, xh2, br.be2);
+                vmul<DPL>(t, wok, kf);                                           // w_o * keep factor
+                vscale<DPL>(t, t, gp);
+                vgate<DPL>(gy2, y2, t);
+                vadd<DPL>(t, gy2, ncB2);
+                vfma<DPL>(t, xh2, ncG2, t);                                      // gy2 - cB2 - xh2 cG2
+                vmul<DPL>(gpp, s2c, t);                                          // d loss / d p
+                vfma<DPL>(gv, gpp, r1, gv);
+                vmul<DPL>(t, gpp, v);
+                vgate<DPL>(gy1, y1, t);
+                vfma<DPL>(t1, gy1, xh1, t1);                                     // g_gamma1
+                vadd<DPL>(t2, t2, gy1);                                          // g_beta1
             }
         GDN_BATCH_LOOP_END
         store_chan<DPL>(g.gV + ((size_t)sp * h.N + i) * h.D, lane, gv);
@@ -1032,9 +1102,10 @@ k_bwd3(HeadArgs h, BwdArgs g, double* __restrict__ part) {
     GDN_TASK_LOOP_BEGIN(h)
         float v[DPL];
         load_chan_vec<DPL>(h.V + (size_t)i * h.D, lane, v);
-        GDN_BATCH_LOOP_BEGIN(h)
+        GDN_BATCH_LOOP_BEGIN2(h, g.gpred, ((h.training && h.p_drop > 0.f) ? (const uint32_t*)h.bits : (const uint32_t*)nullptr))
             BwdSide<DPL> side;
-            side.load(h, g.gpred, i, b0, nb, lane);
+            if (BUF_) side.from_stage(h, sx_, nb, lane);
+            else side.load(h, g.gpred, i, b0, nb, lane);
             for (int rr = 0; rr < nb; ++rr) {
                 const size_t r = (size_t)(b0 + rr) * h.N + i;
                 float a[WP], xh1[DPL], y1[DPL], kf[DPL], pw[WP];
