@@ -22,7 +22,11 @@ gout = torch.rand(B * N, D, device=dev)
 _, nbr = ops.graph_build(V.detach(), K)
 torch.cuda.synchronize()
 for i in range(iters):
+    if i == iters - 1:                      # ncu --profile-from-start off: only the last fwd+bwd is captured
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     out = layer.forward_batched(x, nbr, V)
     out.backward(gout)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")
