@@ -4,12 +4,18 @@
 // Replaces models/graph_layer.py:56,71-74 (lin / head-mean / bias, applied after the
 // aggregation because lin has no bias), models/GDN.py:77-79 (GNNLayer BN+ReLU) and
 // models/GDN.py:171-187 (head), plus autograd of all of it (SURVEY.md section 8 rows
-// a3, a5, a6, a7).  Nothing D-wide is ever written to HBM in the fused path: every pass
-// recomputes Z = Wl.A from the W-wide aggregate A (16x fewer bytes than Z at W=16, D=128),
-// and the BatchNorm batch statistics -- which force grid-wide reductions -- are obtained
+// a3, a5, a6, a7).  In training ONE D-wide activation reaches HBM: the BatchNorm-1 input
+// xh1 = BN1-affine(Wl.A), written by k_fwd_stats2 and read back by k_fwd_out and the three
+// backward passes (reading it beats recomputing Wl.A from the W-wide aggregate A four times
+// on the FMA pipe); eval recomputes and writes nothing D-wide.  The BatchNorm batch
+// statistics -- which force grid-wide reductions -- are obtained
 //   BN1: from the first and second moments of A (Z is affine in A, so its per-channel
 //        mean/variance follow from mean(A) and cov(A): W + W^2 numbers),
-//   BN2: from one recompute pass.
+//   BN2: from the k_fwd_stats2 pass.
+// The two contractions of the lin backward (g_A = g_z.Wl, g_Wl = g_z^T.A) run on the tensor
+// cores (mma_tf32.cuh) for D in {64, 128}, W <= 16; the forward transform stays on the FMA
+// pipe on purpose (the MMA's truncating accumulation biases Z, which the
+// moment-based BN1 statistics do not forgive).
 //
 // Thread mapping: lane <-> DPL = D/32 consecutive channels; a warp walks rows.  The fused
 // passes are sensor-major (a warp owns sensor i and a range of windows b), so V[i,:] stays

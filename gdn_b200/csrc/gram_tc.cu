@@ -6,19 +6,24 @@
 // re-score:
 //   1. k_normalise_split: vn = v / |v| (fp32), split into two bf16 matrices hi + lo = vn
 //      (|vn - hi - lo| <= 2^-18 |vn|).
-//   2. k_gram_tc (this file's tcgen05 kernel): one CTA owns 128 rows and sweeps the columns in
-//      tiles of 64.  Operand tiles arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B, K-major);
-//      one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=64, K=16) for the
-//      three products hi.hi + hi.lo + lo.hi into a double-buffered TMEM accumulator; four epilogue
-//      warps pull the tile out of TMEM with tcgen05.ld (thread <-> row), filter it against the
-//      row's running threshold and keep the best L = K + 8 candidates per row in shared memory.
-//      The [N, N] matrix is never written.  |approx - exact| <= eps = 3e-5 (3 * 2^-18 from the
-//      dropped lo.lo term and the split residuals, plus fp32 accumulation).
-//   3. k_rescore: the L candidates of every row are re-scored with the SAME fp32 fmaf chain the
-//      exact engine uses (graph_build.cu) and ranked (value desc, index asc) -> bit-identical
-//      output.  A row whose 8 spare candidates all sit within 2*eps of the K-th approximate value
-//      could have lost a true neighbour: its 64-row block is flagged and recomputed by the exact
-//      engine (never observed on non-degenerate embeddings; exercised by the tests with duplicates).
+//   2. k_gram_tc (this file's tcgen05 kernel): one CTA owns 128 rows and sweeps its share of the columns
+//      in tiles of 128 (grid = row blocks x column splits).  Operand tiles arrive by TMA
+//      (cp.async.bulk.tensor, SWIZZLE_128B, K-major; one pipeline stage per (tile, k-block)); one elected
+//      thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) for the three products
+//      hi.hi + hi.lo + lo.hi into two TMEM accumulators; two epilogue warpgroups (one per accumulator) pull
+//      their tiles out of TMEM with software-pipelined tcgen05.ld (thread <-> row), filter them against the
+//      row's threshold and append what passes to the (row, segment) candidate buffer in global memory
+//      (L2-resident), compacting it by bit-bisection when it could overflow.  The [N, N] matrix is never
+//      written.  |approx - exact| <= eps = 3e-5 (3 * 2^-18 from the dropped lo.lo term and the split
+//      residuals, plus fp32 accumulation).
+//   3. k_rescore: merges the row's candidate segments (the K + 8 ... K + 16 best approximate values, by
+//      bit-bisection on order-preserving keys with an early exit), re-scores them with the SAME fp32 fmaf
+//      chain the exact engine uses (graph_build.cu; candidate rows staged through shared memory with
+//      coalesced loads) and ranks them (value desc, index asc) -> bit-identical output.  A row whose spare
+//      candidates all sit within 2*eps of the K-th approximate value could have lost a true neighbour, and
+//      a row with fewer than K + 8 candidates had a stale warm-start hint: its 64-row block is flagged and
+//      recomputed by the exact engine (never observed on non-degenerate embeddings; exercised by the tests
+//      with duplicates and absurd hints).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
