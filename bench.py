@@ -305,6 +305,38 @@ def run_ours(args):
                               "includes the device copy of the batch into the graph's static buffers"}
         del stepper, gmodel
 
+    # ---- the same loop fed from a device-resident series (gdn_b200.datasets):
+    # windows are gathered on the GPU from B window indices, nothing crosses PCIe per step but the loss
+    feed_info = None
+    if world == 1 and not args.no_extras:
+        from gdn_b200.datasets import TimeDataset
+        T_feed = W + 1 + 4 * B * max(args.steps, 3)
+        series = torch.rand(N, T_feed, device=dev, generator=g)
+        ds = TimeDataset.from_series(series, None, None, mode="train", config={"slide_win": W, "slide_stride": 1})
+        fgen = torch.Generator(device=dev).manual_seed(7)
+
+        def feed_run(count):
+            out = []
+            it = iter(ds.loader(B, shuffle=True, generator=fgen, drop_last=True))
+            for _ in range(count):
+                bx, by, _, _ = next(it)
+                out.append(trainer.step(bx, by).item())
+            return out
+
+        feed_run(3)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        feed_run(args.steps)
+        f1.record()
+        barrier()
+        feed_ms = f0.elapsed_time(f1)
+        feed_info = {"value": B * args.steps / (feed_ms / 1e3), "unit": UNIT, "ms_per_step": feed_ms / args.steps,
+                     "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                     "what": "train loop fed by gdn_b200.datasets.TimeDataset.loader: series [N, T] resident in HBM, "
+                             "shuffled window batches gathered by gdn_window_batch (datasets/TimeDataset.py:33-62, train.py:66)"}
+        del ds, series
+
     # ---- per-kernel breakdown of the train step (separate, profiled steps)
     lib.gdn_profile_enable(1)
     PSTEPS = 3
@@ -326,6 +358,8 @@ def run_ours(args):
     }
     if graph_info is not None:
         line["cuda_graph"] = graph_info
+    if feed_info is not None:
+        line["device_feed"] = feed_info
     if rank == 0:
         line["clocks"] = clocks
         line["kernels_ms_per_step"] = {k: round(v["ms_per_step"], 5) for k, v in sorted(

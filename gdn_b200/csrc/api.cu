@@ -431,4 +431,14 @@ int gdn_score(const float* pred, const float* gt, int T, int N, double* scores, 
     return launch_score(pred, gt, T, N, scores, top1, stats, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------- data feed
+int gdn_window_batch(const float* series, const float* labels, int N, int T, int W, const int* win_end, int B,
+                     float* x, float* y, float* lab, int* err, void* stream) {
+    GDN_CHECK_ARG(series && win_end && x && y && err, "window_batch: NULL argument");
+    GDN_CHECK_ARG(N >= 1 && W >= 1 && T > W && B >= 1, "window_batch: bad shape N=%d T=%d W=%d B=%d", N, T, W, B);
+    GDN_CHECK_ARG((long long)B * N * W < (1LL << 31), "window_batch: B*N*W must be < 2^31");
+    prof_enter((cudaStream_t)stream, "@window_batch");
+    return launch_window_batch(series, labels, N, T, W, win_end, B, x, y, lab, err, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -68,6 +68,10 @@ int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_
                        int use_tc, float* kth, float margin, cudaStream_t st);
 
 // scoring.cu
+// windows.cu
+int launch_window_batch(const float* series, const float* labels, int N, int T, int W, const int* win_end, int B,
+                        float* x, float* y, float* lab, int* err, cudaStream_t st);
+
 size_t score_ws_bytes(int T, int N);
 int launch_score(const float* pred, const float* gt, int T, int N, double* scores, double* top1, double* stats,
                  void* ws, size_t ws_bytes, cudaStream_t st);

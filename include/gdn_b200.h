@@ -14,6 +14,8 @@
  *                          BN + ReLU + Dropout + Linear(D,1)), train or eval
  *   gdn_fused_bwd          autograd of models/GDN.py:122-187 (train.py:72)
  *   gdn_score              evaluate.py:48-68 + util/data.py:75-82 (+ evaluate.py:134-139)
+ *   gdn_window_batch       datasets/TimeDataset.py:33-62 (+ the per-step transfer train.py:66):
+ *                          window batches gathered from a device-resident series
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name starts with h_; the library
@@ -191,6 +193,14 @@ int    gdn_ctx_alpha(const gdn_dims* d, const int32_t* nbr, const void* ctx, flo
 size_t gdn_score_ws_bytes(int T, int N);
 int    gdn_score(const float* pred, const float* gt, int T, int N, double* scores, double* top1,
                  double* stats, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- data feed (datasets/TimeDataset.py:33-62) ----
+ * series [N, T] float32 and labels [T] float32 (or NULL) stay resident on the device; a batch is B
+ * window-end indices win_end[b] in [W, T):  x[b,i,w] = series[i, win_end[b]-W+w],  y[b,i] = series[i, win_end[b]],
+ * lab[b] = labels[win_end[b]] (lab may be NULL).  err: one int, zero-initialised by the caller; receives
+ * 1 + b of an out-of-range window (the batch rows of that window are left untouched). */
+int    gdn_window_batch(const float* series, const float* labels, int N, int T, int W, const int* win_end, int B,
+                        float* x, float* y, float* lab, int* err, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,37 @@
+"""The window-dataset oracle (oracle/data_oracle.py) against the vectors the reference's own
+datasets/TimeDataset.py produced (tests/golden/timedataset_small.npz, made by oracle/make_golden_data.py)."""
+import numpy as np
+import pytest
+
+from golden_util import load
+from oracle import data_oracle as do
+
+CASES = [("train", 5, 3), ("test", 5, 3), ("train", 1, 1), ("test", 16, 7)]
+
+
+@pytest.mark.parametrize("mode,W,S", CASES)
+def test_oracle_windows_equal_reference(mode, W, S):
+    rec = load("timedataset_small")
+    x, y, lab = do.process(rec["raw"].tolist(), W, S, mode)
+    tag = f"{mode}_w{W}_s{S}"
+    assert np.array_equal(x, rec[tag + "_x"]) and np.array_equal(y, rec[tag + "_y"])
+    assert np.array_equal(lab, rec[tag + "_labels"].astype(np.float64))
+    assert np.array_equal(x[2], rec[tag + "_item2_x"]) and np.array_equal(y[2], rec[tag + "_item2_y"])
+
+
+def test_window_ends_and_float32_rounding():
+    assert do.window_ends(10, 3, 4, "train").tolist() == [3, 7]
+    assert do.window_ends(10, 3, 4, "test").tolist() == [3, 4, 5, 6, 7, 8, 9]
+    assert do.window_ends(3, 3, 1, "test").tolist() == []
+    # lists go through torch.tensor -> float32 before .double(); float64 arrays keep their bits
+    raw = [[0.1, 0.2, 0.3], [0.0, 1.0, 0.0]]
+    x, _, _ = do.process(raw, 1, 1, "test")
+    assert x[0, 0, 0] == np.float64(np.float32(0.1))
+    x64, _, _ = do.process(np.asarray(raw, dtype=np.float64), 1, 1, "test")
+    assert x64[0, 0, 0] == 0.1
+
+
+def test_mirror_refuses_cpu():
+    from gdn_b200.datasets import TimeDataset
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        TimeDataset([[0.0, 1.0], [0.0, 0.0]], None, config={"slide_win": 1, "slide_stride": 1}, device="cpu")

@@ -1,0 +1,96 @@
+"""GPU parity of the device-resident window dataset (csrc/windows.cu, gdn_b200/datasets) against the
+reference's own TimeDataset vectors and the oracle.  Bit-exact (float32 copies)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load
+from oracle import data_oracle as do
+
+pytestmark = pytest.mark.gpu
+CASES = [("train", 5, 3), ("test", 5, 3), ("train", 1, 1), ("test", 16, 7)]
+
+
+def _make(mode, W, S, raw):
+    from gdn_b200.datasets import TimeDataset
+    return TimeDataset(raw, torch.zeros(2, 4, dtype=torch.long), mode=mode, config={"slide_win": W, "slide_stride": S})
+
+
+@pytest.mark.parametrize("mode,W,S", CASES)
+def test_windows_equal_reference_vectors(mode, W, S):
+    rec = load("timedataset_small")
+    ds = _make(mode, W, S, rec["raw"].tolist())
+    tag = f"{mode}_w{W}_s{S}"
+    assert len(ds) == rec[tag + "_x"].shape[0]
+    x, y, lab = ds.batch(torch.arange(len(ds)))
+    assert np.array_equal(x.cpu().numpy(), rec[tag + "_x"].astype(np.float32))     # train.py:66 casts to float
+    assert np.array_equal(y.cpu().numpy(), rec[tag + "_y"].astype(np.float32))
+    assert np.array_equal(lab.cpu().numpy(), rec[tag + "_labels"])
+    assert np.array_equal(ds.labels.numpy(), rec[tag + "_labels"])
+    item = ds[2]                                                                   # reference item protocol
+    assert item[0].dtype == torch.float64 and np.array_equal(item[0].numpy(), rec[tag + "_item2_x"])
+    assert np.array_equal(item[1].numpy(), rec[tag + "_item2_y"]) and item[3].dtype == torch.long
+    assert np.array_equal(ds[-1][0].numpy(), rec[tag + "_x"][-1])
+
+
+def test_loader_batches_subsets_and_shuffle():
+    rng = np.random.default_rng(3)
+    N, T, W = 70, 400, 12
+    raw = np.concatenate([rng.random((N, T)), np.zeros((1, T))], 0).tolist()
+    ds = _make("train", W, 5, raw)
+    xo, yo, _ = do.process(raw, W, 5, "train")
+    seen = []
+    for x, y, lab, ei in ds.loader(32):                                            # ragged last batch
+        assert x.is_cuda and x.dtype == torch.float32 and ei is ds.edge_index
+        seen.append((x.cpu().numpy(), y.cpu().numpy()))
+    assert len(seen) == len(ds.loader(32)) == (len(ds) + 31) // 32
+    assert np.array_equal(np.concatenate([s[0] for s in seen]), xo.astype(np.float32))
+    assert np.array_equal(np.concatenate([s[1] for s in seen]), yo.astype(np.float32))
+    sub = [5, 1, 17, 3]                                                            # Subset semantics (main.py:71-79)
+    (x, y, lab, _), = list(ds.loader(8, indices=sub))
+    assert np.array_equal(x.cpu().numpy(), xo[sub].astype(np.float32))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    got = torch.cat([b[1] for b in ds.loader(16, shuffle=True, generator=g)]).cpu().numpy()
+    assert got.shape == yo.shape and not np.array_equal(got, yo.astype(np.float32))
+    assert np.array_equal(np.sort(got.sum(1)), np.sort(yo.astype(np.float32).sum(1)))   # a permutation of the windows
+    assert len(list(ds.loader(16, drop_last=True))) == len(ds) // 16
+
+
+def test_edges_and_errors():
+    from gdn_b200 import _lib
+    from gdn_b200._lib import ptr
+    raw = [[float(t) for t in range(9)], [0.0] * 9]
+    ds = _make("test", 8, 1, raw)                                                  # a single window: e = 8 = T - 1
+    assert len(ds) == 1
+    x, y, _ = ds.batch([0])
+    assert x.flatten().tolist() == [float(t) for t in range(8)] and y.item() == 8.0
+    x, y, lab = ds.batch([])
+    assert x.shape == (0, 1, 8) and y.shape == (0, 1)
+    with pytest.raises(IndexError):
+        ds.batch([1])
+    with pytest.raises(IndexError):
+        ds.loader(4, indices=[0, 2])
+    assert len(_make("test", 9, 1, raw)) == 0                                       # slide_win == T: no window
+    # the kernel itself flags a window that leaves the series (C ABI contract)
+    lib = _lib.load()
+    ends = torch.tensor([8, 3, 9], dtype=torch.int32, device="cuda")               # 3 < W and 9 >= T are invalid
+    xb = torch.full((3, 1, 8), -1.0, device="cuda"); yb = torch.full((3, 1), -1.0, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = lib.gdn_window_batch(ptr(ds.series), None, 1, 9, 8, ptr(ends), 3, ptr(xb), ptr(yb), None, ptr(err),
+                              torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and err.item() in (2, 3) and yb.flatten().tolist() == [8.0, -1.0, -1.0]
+    assert lib.gdn_window_batch(ptr(ds.series), None, 1, 9, 9, ptr(ends), 3, ptr(xb), ptr(yb), None, ptr(err), None) < 0
+
+
+def test_full_size_property_windows_are_views_of_the_series():
+    """C5-sized feed: every gathered window equals the strided view of the series (size-independent check)."""
+    N, T, W, B = 16384, 512, 16, 64
+    series = torch.rand(N, T, device="cuda")
+    from gdn_b200.datasets import TimeDataset
+    ds = TimeDataset.from_series(series, None, None, mode="test", config={"slide_win": W, "slide_stride": 1})
+    assert len(ds) == T - W
+    idx = torch.randint(0, T - W, (B,), device="cuda")
+    x, y, _ = ds.batch(idx)
+    view = series.unfold(1, W + 1, 1)                                              # [N, T-W, W+1]
+    want = view[:, idx, :].permute(1, 0, 2)
+    assert torch.equal(x, want[..., :W]) and torch.equal(y, want[..., W])
