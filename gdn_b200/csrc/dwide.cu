@@ -687,9 +687,14 @@ struct RowEval {
     __device__ __forceinline__ void eval(const float (&a)[WP], float (&xh1)[DPL], float (&y1)[DPL]) const {
 #pragma unroll
         for (int j = 0; j < DPL; ++j) {
-            float z = 0.f;
+            // two interleaved partial sums over even / odd window taps: one FFMA2 per pair of taps
+            unsigned long long z2 = 0ull;
 #pragma unroll
-            for (int w = 0; w < WP; ++w) z = fmaf(wl[j][w], a[w], z);
+            for (int w = 0; w < WP; w += 2)
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(z2) : "l"(pk2(wl[j][w], wl[j][w + 1])), "l"(pk2(a[w], a[w + 1])));
+            float z0, z1;
+            upk2(z2, z0, z1);
+            const float z = z0 + z1;
             xh1[j] = fmaf(z, k1a[j], k1b[j]);
             y1[j] = fmaf(g1[j], xh1[j], be1[j]);
         }
@@ -870,21 +875,44 @@ k_fwd_out(HeadArgs h, float* __restrict__ pred) {
                 for (int jj = 0; jj < H; ++jj)
                     if (bpart * H + jj < DPL) my_bits[jj] = gen_keep_word<DPL>(h, (size_t)(b0 + brow) * h.N + i, bpart * H + jj);
             }
-#pragma unroll 2
-            for (int rr = 0; rr < nb; ++rr) {
-                float a[WP], xh1[DPL], y1[DPL];
+            // one row: the lane's partial of pred (sum over its DPL channels), packed chain
+            auto row_partial = [&](int rr) -> float {
+                float a[WP], xh1[DPL], y1[DPL], kf[DPL], r1[DPL], p[DPL], xh2[DPL], y2[DPL], r2[DPL], wk[DPL], dv[DPL];
                 row_inputs<DPL, WP, NEED_A_, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
-                float dot = 0.f;
 #pragma unroll
                 for (int j = 0; j < DPL; ++j) {
                     const uint32_t word = __shfl_sync(0xffffffffu, my_bits[j % H], SPLIT ? rr + XH_ROWS * (j / H) : rr);
-                    const float kf = drop ? (((word >> lane) & 1u) ? h.scale : 0.f) : 1.f;
-                    const float p = fmaxf(y1[j], 0.f) * v[j];
-                    const float y2 = fmaf(g2[j], fmaf(p, k2a[j], k2b[j]), be2[j]);
-                    dot = fmaf(fmaxf(y2, 0.f) * kf, wo[j], dot);
+                    kf[j] = drop ? (((word >> lane) & 1u) ? h.scale : 0.f) : 1.f;
                 }
-                dot = warp_sum(dot);
-                if (lane == rr) my_pred = dot + bo;
+                vrelu<DPL>(r1, y1);
+                vmul<DPL>(p, r1, v);
+                vfma<DPL>(xh2, p, k2a, k2b);
+                vfma<DPL>(y2, g2, xh2, be2);
+                vrelu<DPL>(r2, y2);
+                vmul<DPL>(wk, wo, kf);
+                vmul<DPL>(dv, r2, wk);
+                float dot = 0.f;
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) dot += dv[j];
+                return dot;
+            };
+            if (BUF_) {
+                // the batch's XH_ROWS row sums in one butterfly reduce-scatter (9 shuffles instead of 5 per row)
+                float dots[XH_ROWS];
+#pragma unroll
+                for (int rr = 0; rr < XH_ROWS; ++rr) dots[rr] = rr < nb ? row_partial(rr) : 0.f;   // nb is warp-uniform
+                int ridx;
+                const float tot = reduce_scatter<XH_ROWS>(dots, lane, &ridx);
+                // lanes 4r .. 4r+3 now hold the total of row r = ridx; lane r fetches it for the coalesced store below
+                const float mine = __shfl_sync(0xffffffffu, tot, (lane & (XH_ROWS - 1)) * (32 / XH_ROWS));
+                (void)ridx;
+                if (lane < XH_ROWS) my_pred = mine + bo;
+            } else {
+#pragma unroll 2
+                for (int rr = 0; rr < nb; ++rr) {
+                    const float dot = warp_sum(row_partial(rr));
+                    if (lane == rr) my_pred = dot + bo;
+                }
             }
             if (lane < nb) pred[(size_t)(b0 + lane) * h.N + i] = my_pred;
             if (drop && brow < nb) {
@@ -980,17 +1008,19 @@ k_bwd1(HeadArgs h, BwdArgs g, double* __restrict__ part) {
                 row_inputs<DPL, WP, NEED_A_, BUF_>(re, sa_, sx_, rr, lane, a, xh1, y1);
                 const float gp = side.row(h, rr, lane, kf);
                 tb += gp;
-#pragma unroll
-                for (int j = 0; j < DPL; ++j) {
-                    const float p = fmaxf(y1[j], 0.f) * v[j];
-                    const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
-                    const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
-                    const float hm = fmaxf(y2, 0.f) * kf[j];
-                    t0[j] = fmaf(gp, hm, t0[j]);                                  // g_wo
-                    const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
-                    t1[j] = fmaf(gy2, xh2, t1[j]);                                // g_gamma2
-                    t2[j] += gy2;                                                 // g_beta2
-                }
+                // packed chain (pairs of channels per instruction)
+                float r1[DPL], p[DPL], xh2[DPL], y2[DPL], q[DPL], r2[DPL], wq[DPL], gy2[DPL];
+                vrelu<DPL>(r1, y1);
+                vmul<DPL>(p, r1, v);
+                vfma<DPL>(xh2, p, br.k2a, br.k2b);
+                vfma<DPL>(y2, br.g2, xh2, br.be2);
+                vscale<DPL>(q, kf, gp);                                          // g_pred * keep factor
+                vrelu<DPL>(r2, y2);
+                vfma<DPL>(t0, r2, q, t0);                                        // g_wo
+                vmul<DPL>(wq, br.wo, q);
+                vgate<DPL>(gy2, y2, wq);
+                vfma<DPL>(t1, gy2, xh2, t1);                                     // g_gamma2
+                vadd<DPL>(t2, t2, gy2);                                          // g_beta2
             }
         GDN_BATCH_LOOP_END
 #pragma unroll
@@ -1189,6 +1219,9 @@ k_bwd3_mma(HeadArgs h, BwdArgs g, double* __restrict__ part) {
     load_chan<DPL>(g.c1 + h.D, lane, cG1);
 #pragma unroll
     for (int j = 0; j < DPL; ++j) { s2c[j] = br.g2[j] * br.k2a[j]; s1c[j] = re.g1[j] * re.k1a[j]; }
+    float ncB2[DPL], ncG2[DPL], ncB1[DPL], ncG1[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) { ncB2[j] = -cB2[j]; ncG2[j] = -cG2[j]; ncB1[j] = -cB1[j]; ncG1[j] = -cG1[j]; }
     uint2* sW = reinterpret_cast<uint2*>(dyn_smem);
     float* sAcc = reinterpret_cast<float*>(dyn_smem + M::W_BYTES);
     float* sbuf = reinterpret_cast<float*>(dyn_smem + M::W_BYTES + M::ACC_BYTES) + (size_t)wid * 2 * BUF_FLOATS;
@@ -1287,17 +1320,24 @@ k_bwd3_mma(HeadArgs h, BwdArgs g, double* __restrict__ part) {
             load_chan_vec<DPL>(sG + rr * GS, lane, xh1);
             re.from_saved(xh1, y1);
             const float gp = side.row(h, rr, lane, kf);
-#pragma unroll
-            for (int j = 0; j < DPL; ++j) {
-                const float p = fmaxf(y1[j], 0.f) * v[j];
-                const float xh2 = fmaf(p, br.k2a[j], br.k2b[j]);
-                const float y2 = fmaf(br.g2[j], xh2, br.be2[j]);
-                const float gy2 = y2 > 0.f ? gp * br.wo[j] * kf[j] : 0.f;
-                const float gpp = s2c[j] * (gy2 - cB2[j] - xh2 * cG2[j]);
-                const float gy1 = y1[j] > 0.f ? gpp * v[j] : 0.f;
-                gz[j] = s1c[j] * (gy1 - cB1[j] - xh1[j] * cG1[j]);            // d loss / d z
-                gb[j] += gz[j];
-            }
+            // packed chain (pairs of channels per instruction)
+            float r1[DPL], p[DPL], xh2[DPL], y2[DPL], t[DPL], gy2[DPL], gpp[DPL], gy1[DPL];
+            vrelu<DPL>(r1, y1);
+            vmul<DPL>(p, r1, v);
+            vfma<DPL>(xh2, p, br.k2a, br.k2b);
+            vfma<DPL>(y2, br.g2, xh2, br.be2);
+            vmul<DPL>(t, br.wo, kf);
+            vscale<DPL>(t, t, gp);
+            vgate<DPL>(gy2, y2, t);
+            vadd<DPL>(t, gy2, ncB2);
+            vfma<DPL>(t, xh2, ncG2, t);                                          // gy2 - cB2 - xh2 cG2
+            vmul<DPL>(gpp, s2c, t);
+            vmul<DPL>(t, gpp, v);
+            vgate<DPL>(gy1, y1, t);
+            vadd<DPL>(t, gy1, ncB1);
+            vfma<DPL>(t, xh1, ncG1, t);                                          // gy1 - cB1 - xh1 cG1
+            vmul<DPL>(gz, s1c, t);                                               // d loss / d z
+            vadd<DPL>(gb, gb, gz);
             store_chan<DPL>(sG + rr * GS, lane, gz);                            // in place
         }
         if (nb < TR) {                                                        // tail: zero rows for the MMAs
