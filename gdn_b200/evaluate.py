@@ -13,12 +13,24 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _scores_for(pred, gt):
-    """pred, gt: array-likes [T, N] -> scores [N, T] float64 (numpy)."""
+def _pred_gt(result):
+    """[pred, gt, labels] ([3][T][N] nested lists / arrays, or a gdn_b200.test.TestResult whose device copies
+    are used as they are: no host round trip) -> (pred, gt) float32 CUDA tensors [T, N]."""
     dev = _device()
-    p = torch.as_tensor(np.asarray(pred, dtype=np.float32)).to(dev)
-    g = torch.as_tensor(np.asarray(gt, dtype=np.float32)).to(dev)
-    scores, _, _ = ops.score(p, g, want_scores=True, want_top1=False)
+    held = getattr(result, "device_tensors", None)
+    if held is not None:
+        return held[0].to(dev, torch.float32).contiguous(), held[1].to(dev, torch.float32).contiguous()
+    arr = np.asarray([np.asarray(result[0], dtype=np.float32), np.asarray(result[1], dtype=np.float32)])
+    return torch.as_tensor(arr[0]).to(dev), torch.as_tensor(arr[1]).to(dev)
+
+
+def _scores_for(pred, gt):
+    """pred, gt: array-likes or tensors [T, N] -> scores [N, T] float64 (numpy)."""
+    dev = _device()
+    p = pred if torch.is_tensor(pred) else torch.as_tensor(np.asarray(pred, dtype=np.float32))
+    g = gt if torch.is_tensor(gt) else torch.as_tensor(np.asarray(gt, dtype=np.float32))
+    scores, _, _ = ops.score(p.to(dev, torch.float32).contiguous(), g.to(dev, torch.float32).contiguous(),
+                             want_scores=True, want_top1=False)
     return scores.cpu().numpy()
 
 
@@ -33,19 +45,14 @@ def get_err_scores(test_res, val_res):
 def get_full_err_scores(test_result, val_result):
     """evaluate.py:6-36: [pred, gt, labels] nested lists ([3][T][N]) for the test and the
     validation run -> (all_scores [N, T], all_normals [N, Tv]) float64."""
-    np_test = np.asarray(test_result, dtype=np.float32)
-    np_val = np.asarray(val_result, dtype=np.float32)
-    all_scores = _scores_for(np_test[0], np_test[1])
-    all_normals = _scores_for(np_val[0], np_val[1])
+    all_scores = _scores_for(*_pred_gt(test_result))
+    all_normals = _scores_for(*_pred_gt(val_result))
     return all_scores, all_normals
 
 
 def get_final_err_scores(test_result, val_result):
     """evaluate.py:39-44 as intended (the reference version passes a keyword
     get_full_err_scores does not accept): per-tick maximum over sensors."""
-    dev = _device()
-    np_test = np.asarray(test_result, dtype=np.float32)
-    p = torch.as_tensor(np_test[0]).to(dev)
-    g = torch.as_tensor(np_test[1]).to(dev)
+    p, g = _pred_gt(test_result)
     _, top1, _ = ops.score(p, g, want_scores=False, want_top1=True)
     return top1.cpu().numpy()

@@ -26,3 +26,16 @@ def process(raw_data, slide_win, slide_stride, mode):
     x = np.stack([data[:, e - slide_win:e] for e in ends]) if len(ends) else np.zeros((0, data.shape[0], slide_win))
     y = np.stack([data[:, e] for e in ends]) if len(ends) else np.zeros((0, data.shape[0]))
     return x, y, labels[ends].astype(np.float32).astype(np.float64)   # torch.Tensor(labels_arr) is float32 (:58)
+
+
+def test_loop(predict_batches, y_batches, label_batches):
+    """test.py:20-75 given the per-batch model outputs: avg_loss = mean over batches of the float32
+    MSELoss(reduction='mean') values (:49-50, :66-67, :75), and the concatenated [pred, gt, labels] with the
+    labels repeated per sensor (:53-63).  Inputs: lists of float32 arrays [b, N], [b, N], [b]."""
+    losses = [float(np.mean((p.astype(np.float32) - y.astype(np.float32)) ** 2, dtype=np.float32))
+              for p, y in zip(predict_batches, y_batches)]
+    pred = np.concatenate(predict_batches).astype(np.float32)
+    gt = np.concatenate(y_batches).astype(np.float32)
+    labels = np.concatenate([np.repeat(l.astype(np.float32)[:, None], p.shape[1], axis=1)
+                             for l, p in zip(label_batches, predict_batches)])
+    return sum(losses) / len(losses), [pred, gt, labels]

@@ -35,3 +35,19 @@ def test_mirror_refuses_cpu():
     from gdn_b200.datasets import TimeDataset
     with pytest.raises(RuntimeError, match="no CPU path"):
         TimeDataset([[0.0, 1.0], [0.0, 0.0]], None, config={"slide_win": 1, "slide_stride": 1}, device="cpu")
+
+
+def test_test_loop_oracle_equals_reference():
+    """oracle test_loop (test.py:20-75) fed with the reference's own per-batch predictions reproduces the
+    reference's avg_loss and result lists (tests/golden/test_loop_small.npz, oracle/make_golden_test.py)."""
+    rec = load("test_loop_small")
+    B = int(rec["dims"][5])
+    pred, gt, labels = rec["pred"], rec["gt"], rec["labels"]
+    cuts = list(range(0, len(pred), B))
+    avg, (p, g, l) = do.test_loop([pred[c:c + B] for c in cuts], [gt[c:c + B] for c in cuts], [labels[c:c + B, 0] for c in cuts])
+    assert abs(avg - float(rec["avg_loss"])) <= 2e-7 * abs(float(rec["avg_loss"]))
+    assert np.array_equal(p, pred) and np.array_equal(g, gt) and np.array_equal(l, labels)
+    # ground truth and labels of the loop are the dataset's windows
+    N, T, W = (int(v) for v in rec["dims"][:3])
+    _, y, lab = do.process(rec["raw"].tolist(), W, 1, "test")
+    assert np.array_equal(gt, y.astype(np.float32)) and np.array_equal(labels[:, 0], lab.astype(np.float32))

@@ -94,3 +94,37 @@ def test_full_size_property_windows_are_views_of_the_series():
     view = series.unfold(1, W + 1, 1)                                              # [N, T-W, W+1]
     want = view[:, idx, :].permute(1, 0, 2)
     assert torch.equal(x, want[..., :W]) and torch.equal(y, want[..., W])
+
+
+def test_test_loop_matches_reference():
+    """gdn_b200.test.test (test.py:20-75) over the device-resident loader, reference weights loaded: the
+    reference's avg_loss / predictions within 1e-4, ground truth and labels exact; the result feeds the scorer
+    without leaving the device and equals scoring the reference's lists."""
+    from gdn_b200.datasets import TimeDataset
+    from gdn_b200.evaluate import get_full_err_scores
+    from gdn_b200.models.GDN import GDN
+    from gdn_b200.test import test
+    rec = load("test_loop_small")
+    N, T, W, K, D, B = (int(v) for v in rec["dims"])
+    ei = torch.zeros(2, 1, dtype=torch.long)
+    ds = TimeDataset(rec["raw"].tolist(), ei, mode="test", config={"slide_win": W, "slide_stride": 1})
+    model = GDN([ei], N, dim=D, input_dim=W, topk=K)
+    model.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in rec.items() if k.startswith("sd.")})
+    model = model.cuda()
+    avg, res = test(model, ds.loader(B))
+    assert abs(avg - float(rec["avg_loss"])) <= 1e-4 * abs(float(rec["avg_loss"]))
+    assert len(res) == 3 and res[0].shape == rec["pred"].shape and not res[0].is_cuda
+    assert np.abs(res[0].numpy() - rec["pred"]).max() <= 1e-4 * np.abs(rec["pred"]).max()
+    assert np.array_equal(res[1].numpy(), rec["gt"]) and np.array_equal(res[2].numpy(), rec["labels"])
+    assert np.asarray(res).shape == (3,) + rec["pred"].shape                       # main.py:get_score does np.array(...)
+    # a second pass with ragged batches, and the reference's DataLoader protocol (CPU doubles per item)
+    avg2, res2 = test(model, ds.loader(7))
+    assert torch.equal(res2[1], res[1]) and np.abs(res2[0].numpy() - res[0].numpy()).max() <= 1e-6
+    dl = torch.utils.data.DataLoader(ds, batch_size=B, shuffle=False)
+    avg3, res3 = test(model, dl)
+    assert abs(avg3 - avg) <= 1e-6 * abs(avg) and torch.equal(res3[1], res[1])
+    s_dev, n_dev = get_full_err_scores(res, res)
+    s_ref, _ = get_full_err_scores([res[0].tolist(), res[1].tolist(), res[2].tolist()], [rec["pred"], rec["gt"], rec["labels"]])
+    assert np.array_equal(s_dev, s_ref) and np.array_equal(s_dev, n_dev)
+    with pytest.raises(RuntimeError, match="no batch"):
+        test(model, [])
