@@ -431,6 +431,29 @@ int gdn_score(const float* pred, const float* gt, int T, int N, double* scores, 
     return launch_score(pred, gt, T, N, scores, top1, stats, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------- metrics
+int gdn_f1_sweep(const double* sorted_scores, const float* labels_sorted, int T, const int* k_pred, const int* k_thr,
+                 int S, double* fmeas, double* thresholds, void* stream) {
+    GDN_CHECK_ARG(sorted_scores && labels_sorted && k_pred && k_thr && fmeas && thresholds, "f1_sweep: NULL argument");
+    GDN_CHECK_ARG(T >= 1 && S >= 1 && S <= 65535, "f1_sweep: bad shape T=%d steps=%d", T, S);
+    prof_enter((cudaStream_t)stream, "@f1_sweep");
+    return launch_f1_sweep(sorted_scores, labels_sorted, T, k_pred, k_thr, S, fmeas, thresholds, (cudaStream_t)stream);
+}
+
+int gdn_binary_counts(const double* scores, const float* labels, int T, double threshold, unsigned long long* counts,
+                      void* stream) {
+    GDN_CHECK_ARG(scores && labels && counts && T >= 1, "binary_counts: bad argument");
+    prof_enter((cudaStream_t)stream, "@binary_counts");
+    return launch_binary_counts(scores, labels, T, threshold, counts, (cudaStream_t)stream);
+}
+
+int gdn_auc_ranksum(const double* sorted_scores, const float* labels_sorted, int T, double* ranksum,
+                    unsigned long long* npos, void* stream) {
+    GDN_CHECK_ARG(sorted_scores && labels_sorted && ranksum && npos && T >= 1, "auc_ranksum: bad argument");
+    prof_enter((cudaStream_t)stream, "@auc_ranksum");
+    return launch_auc_ranksum(sorted_scores, labels_sorted, T, ranksum, npos, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------- data feed
 int gdn_window_batch(const float* series, const float* labels, int N, int T, int W, const int* win_end, int B,
                      float* x, float* y, float* lab, int* err, void* stream) {

@@ -68,6 +68,14 @@ int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_
                        int use_tc, float* kth, float margin, cudaStream_t st);
 
 // scoring.cu
+// metrics.cu
+int launch_f1_sweep(const double* sorted_scores, const float* labels_sorted, int T, const int* k_pred, const int* k_thr,
+                    int S, double* fmeas, double* thresholds, cudaStream_t st);
+int launch_binary_counts(const double* scores, const float* labels, int T, double threshold, unsigned long long* counts,
+                         cudaStream_t st);
+int launch_auc_ranksum(const double* sorted_scores, const float* labels_sorted, int T, double* ranksum,
+                       unsigned long long* npos, cudaStream_t st);
+
 // windows.cu
 int launch_window_batch(const float* series, const float* labels, int N, int T, int W, const int* win_end, int B,
                         float* x, float* y, float* lab, int* err, cudaStream_t st);

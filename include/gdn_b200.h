@@ -14,6 +14,9 @@
  *                          BN + ReLU + Dropout + Linear(D,1)), train or eval
  *   gdn_fused_bwd          autograd of models/GDN.py:122-187 (train.py:72)
  *   gdn_score              evaluate.py:48-68 + util/data.py:75-82 (+ evaluate.py:134-139)
+ *   gdn_f1_sweep, gdn_binary_counts, gdn_auc_ranksum
+ *                          util/data.py:28-51 (eval_scores) and evaluate.py:129-158
+ *                          (get_best_performance_data): threshold sweep / F1, precision, recall, AUC
  *   gdn_window_batch       datasets/TimeDataset.py:33-62 (+ the per-step transfer train.py:66):
  *                          window batches gathered from a device-resident series
  *
@@ -193,6 +196,20 @@ int    gdn_ctx_alpha(const gdn_dims* d, const int32_t* nbr, const void* ctx, flo
 size_t gdn_score_ws_bytes(int T, int N);
 int    gdn_score(const float* pred, const float* gt, int T, int N, double* scores, double* top1,
                  double* stats, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- evaluation metrics (util/data.py:28-51, evaluate.py:129-158) ----
+ * sorted_scores [T] float64 ascending (stable), labels_sorted [T] float32 in {0,1} in the same order.
+ * gdn_f1_sweep: for each of S steps, ticks at sorted positions >= k_pred[s] are predicted anomalous:
+ *   fmeas[s] = 2 TP / (P + T - k_pred[s]) (0 if the denominator is 0), thresholds[s] = sorted_scores[k_thr[s]]
+ *   (NaN if k_thr[s] is outside [0, T)).
+ * gdn_binary_counts: counts[0..3] = TP, FP, FN, TN of (scores[t] > threshold) against labels[t] (unsorted is fine).
+ * gdn_auc_ranksum: ranksum = sum over positive ticks of their tie-averaged 1-based rank, npos = number of positives. */
+int    gdn_f1_sweep(const double* sorted_scores, const float* labels_sorted, int T, const int* k_pred, const int* k_thr,
+                    int S, double* fmeas, double* thresholds, void* stream);
+int    gdn_binary_counts(const double* scores, const float* labels, int T, double threshold, unsigned long long* counts,
+                         void* stream);
+int    gdn_auc_ranksum(const double* sorted_scores, const float* labels_sorted, int T, double* ranksum,
+                       unsigned long long* npos, void* stream);
 
 /* ---- data feed (datasets/TimeDataset.py:33-62) ----
  * series [N, T] float32 and labels [T] float32 (or NULL) stay resident on the device; a batch is B
