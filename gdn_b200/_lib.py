@@ -50,6 +50,8 @@ SIGNATURES = {
     "gdn_graph_build": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_size_t, C.c_int, c_fp]),
     "gdn_graph_build_warm": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_size_t, C.c_int, c_fp,
                                        C.c_float, c_fp]),
+    "gdn_graph_build_rows": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_fp, c_fp, c_fp, C.c_size_t,
+                                       C.c_int, c_fp, C.c_float, c_fp]),
     "gdn_graphlayer_ctx_bytes": (C.c_size_t, [_P(Dims)]),
     "gdn_graphlayer_ws_bytes": (C.c_size_t, [_P(Dims)]),
     "gdn_graphlayer_fwd": (C.c_int, [_P(Dims), c_fp, c_fp, c_fp, _P(LayerParams), c_fp, c_fp, c_fp, c_fp,

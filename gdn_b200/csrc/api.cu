@@ -258,7 +258,7 @@ int gdn_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* 
     GDN_CHECK_ARG(V != nullptr, "V is NULL");
     GDN_CHECK_ARG(N >= 1 && D >= 1 && K >= 1 && K <= N, "graph_build: bad shape N=%d D=%d K=%d", N, D, K);
     prof_enter((cudaStream_t)stream, "@graph_build");
-    return launch_graph_build(V, N, D, K, idx, nbr, ws, ws_bytes, use_tensor_cores, nullptr, 0.f, (cudaStream_t)stream);
+    return launch_graph_build(V, N, D, K, 0, N, idx, nbr, ws, ws_bytes, use_tensor_cores, nullptr, 0.f, (cudaStream_t)stream);
 }
 
 int gdn_graph_build_warm(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, size_t ws_bytes,
@@ -267,7 +267,17 @@ int gdn_graph_build_warm(const float* V, int N, int D, int K, int64_t* idx, int3
     GDN_CHECK_ARG(N >= 1 && D >= 1 && K >= 1 && K <= N, "graph_build: bad shape N=%d D=%d K=%d", N, D, K);
     GDN_CHECK_ARG(kth != nullptr && margin >= 0.f, "graph_build_warm: kth is NULL or margin < 0");
     prof_enter((cudaStream_t)stream, "@graph_build");
-    return launch_graph_build(V, N, D, K, idx, nbr, ws, ws_bytes, use_tensor_cores, kth, margin, (cudaStream_t)stream);
+    return launch_graph_build(V, N, D, K, 0, N, idx, nbr, ws, ws_bytes, use_tensor_cores, kth, margin, (cudaStream_t)stream);
+}
+
+int gdn_graph_build_rows(const float* V, int N, int D, int K, int row0, int row1, int64_t* idx, int32_t* nbr, void* ws,
+                         size_t ws_bytes, int use_tensor_cores, float* kth, float margin, void* stream) {
+    GDN_CHECK_ARG(V != nullptr, "V is NULL");
+    GDN_CHECK_ARG(N >= 1 && D >= 1 && K >= 1 && K <= N, "graph_build: bad shape N=%d D=%d K=%d", N, D, K);
+    GDN_CHECK_ARG(kth == nullptr || margin >= 0.f, "graph_build_rows: margin < 0");
+    prof_enter((cudaStream_t)stream, "@graph_build");
+    return launch_graph_build(V, N, D, K, row0, row1, idx, nbr, ws, ws_bytes, use_tensor_cores, kth, margin,
+                              (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------- GraphLayer (shared graph)

@@ -38,7 +38,7 @@ constexpr int TC_BN = 128;        // columns per tile = UMMA N (N < 128 leaves t
 constexpr int TC_BK = 64;         // bf16 per k-block: 128 bytes = one SWIZZLE_128B atom row
 constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 384;
-constexpr int TC_MAXSPLIT = 4;     // column splits per row block (x 2 warpgroups = candidate segments per row)
+constexpr int TC_MAXSPLIT = 8;     // column splits per row block (x 2 warpgroups = candidate segments per row)
 constexpr int TC_SLACK = 8;
 constexpr int TC_MAXL = 80;
 constexpr int TC_MAXC = 256;      // buffer capacity (8 entries per lane in a compaction)
@@ -170,7 +170,7 @@ __global__ void k_normalise_split(const float* __restrict__ V, int N, int D, flo
 // candidate segment of every row: segment = 2 * blockIdx.y + g, merged by k_rescore.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-          int N, int KB, int L, int C, int tiles_per_split, float* __restrict__ bufv, int* __restrict__ bufj,
+          int N, int KB, int L, int C, int tiles_per_split, int rb0, float* __restrict__ bufv, int* __restrict__ bufj,
           int* __restrict__ rowcnt, const float* __restrict__ hint, float margin, int* __restrict__ err, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;        // SWIZZLE_128B atoms: 1024-byte aligned
@@ -188,7 +188,8 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * TC_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TC_BM;
+    const int m0 = (blockIdx.x + rb0) * TC_BM;                          // global first row (rb0: first row block of the range)
+    const int l0 = blockIdx.x * TC_BM;                                   // ... and its position in the candidate buffers
     const int S = 2 * (int)gridDim.y;                                    // candidate segments per row
     const int tile0 = blockIdx.y * tiles_per_split;                      // this CTA sweeps tiles [tile0, tile0 + ntiles)
     const int ntiles = min(tiles_per_split, (N + TC_BN - 1) / TC_BN - tile0);
@@ -274,8 +275,8 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
         const int seg = 2 * (int)blockIdx.y + wg;    // candidate segment of this (column split, warpgroup)
         const int wrow0 = (warp & 3) * 32;           // first row of this warp inside the CTA (= its TMEM lanes)
         const int row = wrow0 + lane;
-        float* bv = bufv + ((size_t)(m0 + row) * S + seg) * C;
-        int* bj = bufj + ((size_t)(m0 + row) * S + seg) * C;
+        float* bv = bufv + ((size_t)(l0 + row) * S + seg) * C;
+        int* bj = bufj + ((size_t)(l0 + row) * S + seg) * C;
         float* pv = p_vals + wg * 16 * TC_BM + row;  // staging slot q of row r at [q * 128 + r]
         int cnt = 0;
         // Warm start: the caller may pass last step's K-th cosine per row.  The embedding moves by one
@@ -304,8 +305,8 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
                 const int rr = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int cnt_r = __shfl_sync(0xffffffffu, cnt, rr);
-                float* gv = bufv + ((size_t)(m0 + wrow0 + rr) * S + seg) * C;
-                int* gj = bufj + ((size_t)(m0 + wrow0 + rr) * S + seg) * C;
+                float* gv = bufv + ((size_t)(l0 + wrow0 + rr) * S + seg) * C;
+                int* gj = bufj + ((size_t)(l0 + wrow0 + rr) * S + seg) * C;
                 unsigned key[NE];
                 int ej[NE];
 #pragma unroll
@@ -412,7 +413,7 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
                 if (!(dbg & 1)) filter(rb, j0 + (grp + 1) * 16);
             }
         }
-        if (ok && m0 + row < N) rowcnt[(size_t)(m0 + row) * S + seg] = cnt;
+        if (ok && m0 + row < N) rowcnt[(size_t)(l0 + row) * S + seg] = cnt;
     }
     tc_fence_before();
     __syncthreads();
@@ -436,7 +437,7 @@ __device__ __forceinline__ float key2f(unsigned k) { return __uint_as_float(k ^ 
 
 template <int D>
 __global__ void __launch_bounds__(RS_WARPS * 32)
-k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int K, int L, int C, int S,
+k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int row0, int row1, int K, int L, int C, int S,
           const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ rowcnt,
           float* __restrict__ kth_out,
           int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, int* __restrict__ block_flags) {
@@ -446,8 +447,9 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int
     __shared__ int s_out[RS_WARPS][TC_MAXL];
     extern __shared__ __align__(16) float rs_smem[];        // per warp: tile [32][D+4] (first the pool keys/idx [2][S*L]), v_i [D]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int i = blockIdx.x * RS_WARPS + wid;
-    if (i >= N) return;
+    const int li = blockIdx.x * RS_WARPS + wid;               // row inside the range = row of the candidate buffers
+    const int i = row0 + li;
+    if (i >= row1) return;
     constexpr int TS = D + 4;                                    // tile row stride: conflict-free float4 row reads
     float* tile = rs_smem + (size_t)wid * (32 * TS + D);
     float* svi = tile + 32 * TS;
@@ -459,7 +461,7 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int
     for (int k = lane; k < K; k += 32) s_out[wid][k] = i;     // placeholder if the row is short (it is flagged)
     // ---- merge the row's candidate segments: the L best approximate values of their union ----
     // (segment counts first, then one flat pass over all segments so that every load is independent)
-    int my_cnt = lane < S ? min(rowcnt[(size_t)i * S + lane], L) : 0;     // S <= 2 * TC_MAXSPLIT <= 32
+    int my_cnt = lane < S ? min(rowcnt[(size_t)li * S + lane], L) : 0;    // S <= 2 * TC_MAXSPLIT <= 32
     int my_off = my_cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -473,7 +475,7 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int N, int
         const int sg = min(f / L, S - 1), e = f - sg * L;
         const int c = __shfl_sync(0xffffffffu, my_cnt, sg), off = __shfl_sync(0xffffffffu, my_off, sg);
         if (e < c) {
-            const size_t src = ((size_t)i * S + sg) * C + e;
+            const size_t src = ((size_t)li * S + sg) * C + e;
             pk[off + e] = f2key(__ldg(cand_val + src));
             pj[off + e] = __ldg(cand_idx + src);
         }
@@ -644,45 +646,55 @@ bool gram_tc_supported(int N, int D, int K) {
     return N >= 1024 && (D == 64 || D == 128) && K + TC_SLACK <= TC_MAXL && K + TC_SLACK <= N;
 }
 
-// column splits per row block: fill the SMs when there are few row blocks (N = 4096 -> 32 blocks x 4)
-static void tc_split(int N, int* nsplit, int* tiles_per_split) {
-    const int blocks = ceil_div(N, TC_BM), ntiles = ceil_div(N, TC_BN);
+// column splits per row block: fill the SMs when there are few row blocks (N = 4096 -> 32 blocks x 4; a rank's
+// eighth of N = 16384 -> 16 blocks x 8); bounded by what the re-score's merge pool holds
+static void tc_split(int N, int D, int K, int blocks, int* nsplit, int* tiles_per_split) {
+    const int ntiles = ceil_div(N, TC_BN), L = K + TC_SLACK;
     int want = num_sms() / blocks;
     if (want < 1) want = 1;
     if (want > TC_MAXSPLIT) want = TC_MAXSPLIT;
+    while (want > 1 && 2 * (2 * want) * L > 32 * (D + 4)) --want;
     const int tps = ceil_div(ntiles, want);
     *tiles_per_split = tps;
     *nsplit = ceil_div(ntiles, tps);
 }
+// candidate-buffer capacity in (128-row block x column split) units: covers the full build and any row range
+static size_t tc_units(int N, int D, int K) {
+    int nsplit, tps;
+    const int blocks = ceil_div(N, TC_BM);
+    tc_split(N, D, K, blocks, &nsplit, &tps);
+    size_t u = (size_t)blocks * nsplit;
+    const size_t floor_u = (size_t)num_sms() + TC_MAXSPLIT;           // blocks_sub * nsplit_sub <= max(num_sms, blocks_sub)
+    return u > floor_u ? u : floor_u;
+}
 
 size_t gram_tc_ws_bytes(int N, int D, int K) {
     const int C = TC_MAXC;
-    (void)K;
-    int nsplit, tps;
-    tc_split(N, &nsplit, &tps);
-    const size_t Npad = (size_t)ceil_div(N, TC_BM) * TC_BM, S = 2 * (size_t)nsplit;
+    const size_t units = tc_units(N, D, K);
     size_t b = align_up((size_t)N * sizeof(float), 256);
     b += 2 * align_up((size_t)N * D * sizeof(__nv_bfloat16), 256);
-    b += 2 * align_up(Npad * S * C * sizeof(float), 256);
-    b += align_up(Npad * S * sizeof(int), 256);
+    b += 2 * align_up(units * TC_BM * 2 * C * sizeof(float), 256);
+    b += align_up(units * TC_BM * 2 * sizeof(int), 256);
     b += align_up(((size_t)(N + 63) / 64 + 68) * sizeof(int), 256);
     return b;
 }
 
-int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, cudaStream_t st,
-                   float* kth, float margin, float** nrm_out, int** flags_out) {
+int launch_gram_tc(const float* V, int N, int D, int K, int row0, int row1, int64_t* idx, int32_t* nbr, void* ws,
+                   cudaStream_t st, float* kth, float margin, float** nrm_out, int** flags_out) {
     const int L = K + TC_SLACK, C = TC_MAXC, KB = D / TC_BK;
+    const int rb0 = row0 / TC_BM, blocks = ceil_div(row1, TC_BM) - rb0;
     int nsplit, tps;
-    tc_split(N, &nsplit, &tps);
+    tc_split(N, D, K, blocks, &nsplit, &tps);
     const int S = 2 * nsplit;
-    const size_t Npad = (size_t)ceil_div(N, TC_BM) * TC_BM;
+    const size_t units = tc_units(N, D, K);
+    GDN_CHECK_ARG((size_t)blocks * nsplit <= units, "gram_tc: %d row blocks x %d splits exceed the workspace", blocks, nsplit);
     char* p = (char*)ws;
     float* nrm = (float*)p;                 p += align_up((size_t)N * sizeof(float), 256);
     __nv_bfloat16* hi = (__nv_bfloat16*)p;  p += align_up((size_t)N * D * sizeof(__nv_bfloat16), 256);
     __nv_bfloat16* lo = (__nv_bfloat16*)p;  p += align_up((size_t)N * D * sizeof(__nv_bfloat16), 256);
-    float* bufv = (float*)p;                p += align_up(Npad * S * C * sizeof(float), 256);
-    int* bufj = (int*)p;                    p += align_up(Npad * S * C * sizeof(float), 256);
-    int* rowcnt = (int*)p;                  p += align_up(Npad * S * sizeof(int), 256);
+    float* bufv = (float*)p;                p += align_up(units * TC_BM * 2 * C * sizeof(float), 256);
+    int* bufj = (int*)p;                    p += align_up(units * TC_BM * 2 * C * sizeof(float), 256);
+    int* rowcnt = (int*)p;                  p += align_up(units * TC_BM * 2 * sizeof(int), 256);
     int* flags = (int*)p;                   // [ceil(N/64)] block flags, then the error word
     const int nblk64 = (N + 63) / 64;
     int* err = flags + nblk64;
@@ -714,16 +726,16 @@ int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* n
     if (e != cudaSuccess) return cuda_fail(e, "smem attr k_gram_tc");
     static int dbg = -1;
     if (dbg < 0) { const char* e_ = getenv("GDN_TC_DBG"); dbg = e_ ? atoi(e_) : 0; }
-    k_gram_tc<<<dim3(ceil_div(N, TC_BM), nsplit), TC_THREADS, smem, st>>>(tm_hi, tm_lo, N, KB, L, C, tps, bufv, bufj, rowcnt,
-                                                                          kth, margin, err, dbg);
+    k_gram_tc<<<dim3(blocks, nsplit), TC_THREADS, smem, st>>>(tm_hi, tm_lo, N, KB, L, C, tps, rb0, bufv, bufj, rowcnt, kth,
+                                                              margin, err, dbg);
     GDN_CHECK_LAUNCH("k_gram_tc");
     GDN_CHECK_ARG(2 * S * L <= 32 * (D + 4), "gram_tc: candidate pool (%d) exceeds the re-score tile", 2 * S * L);
     const size_t rs_smem = (size_t)RS_WARPS * (32 * (D + 4) + D) * sizeof(float);
     auto rescore = D == 128 ? k_rescore<128> : k_rescore<64>;
     e = ensure_dyn_smem_ptr(reinterpret_cast<const void*>(rescore), rs_smem);
     if (e != cudaSuccess) return cuda_fail(e, "smem attr k_rescore");
-    rescore<<<ceil_div(N, RS_WARPS), RS_WARPS * 32, rs_smem, st>>>(V, nrm, N, K, L, C, S, bufv, bufj, rowcnt, kth, idx,
-                                                                  nbr, flags);
+    rescore<<<ceil_div(row1 - row0, RS_WARPS), RS_WARPS * 32, rs_smem, st>>>(V, nrm, row0, row1, K, L, C, S, bufv, bufj, rowcnt,
+                                                                            kth, idx, nbr, flags);
     GDN_CHECK_LAUNCH("k_rescore");
     *nrm_out = nrm;
     *flags_out = flags;

@@ -75,10 +75,11 @@ __device__ __forceinline__ void list_insert(float* vals, int* idxs, int* cnt_p, 
 
 // dynamic smem: lists  vals[GB_TI][K] (float), idxs[GB_TI][K] (int)
 __global__ void __launch_bounds__(256)
-k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, int D, int K,
+k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, int D, int K, int blk0,
             int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, const int* __restrict__ block_flags,
             float* __restrict__ kth_out) {
-    if (block_flags != nullptr && block_flags[blockIdx.x] == 0) return;   // fix-up mode: flagged blocks only
+    const int blk = blockIdx.x + blk0;                                     // 64-row block (blk0: first block of the row range)
+    if (block_flags != nullptr && block_flags[blk] == 0) return;           // fix-up mode: flagged blocks only
     __shared__ float As[GB_TI][GB_DC + 1];
     __shared__ float Bs[GB_TJ][GB_DC + 1];
     __shared__ float Cs[GB_TI][GB_TJ + 1];
@@ -89,7 +90,7 @@ k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, i
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ty = tid >> 4, tx = tid & 15;
-    const int i0 = blockIdx.x * GB_TI;
+    const int i0 = blk * GB_TI;
     if (tid < GB_TI) cnts[tid] = 0;
     __syncthreads();
 
@@ -187,8 +188,8 @@ k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, i
 // gram_tc.cu
 bool gram_tc_supported(int N, int D, int K);
 size_t gram_tc_ws_bytes(int N, int D, int K);
-int launch_gram_tc(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, cudaStream_t st,
-                   float* kth, float margin, float** nrm_out, int** flags_out);
+int launch_gram_tc(const float* V, int N, int D, int K, int row0, int row1, int64_t* idx, int32_t* nbr, void* ws,
+                   cudaStream_t st, float* kth, float margin, float** nrm_out, int** flags_out);
 
 size_t graph_build_ws_bytes(int N, int D, int K) {
     size_t b = align_up((size_t)N * sizeof(float), 256);
@@ -199,9 +200,13 @@ size_t graph_build_ws_bytes(int N, int D, int K) {
     return b;
 }
 
-int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, size_t ws_bytes,
-                       int use_tc, float* kth, float margin, cudaStream_t st) {
+// rows [row0, row1) of the graph only (row0 a multiple of 128, row1 a multiple of 128 or N): the row-sharded
+// build of the data-parallel trainer; rows outside the range are not touched
+int launch_graph_build(const float* V, int N, int D, int K, int row0, int row1, int64_t* idx, int32_t* nbr, void* ws,
+                       size_t ws_bytes, int use_tc, float* kth, float margin, cudaStream_t st) {
     GDN_CHECK_ARG(K <= GB_MAXK, "topk K=%d unsupported (max %d)", K, GB_MAXK);
+    GDN_CHECK_ARG(0 <= row0 && row0 < row1 && row1 <= N && row0 % 128 == 0 && (row1 % 128 == 0 || row1 == N),
+                  "graph_build: row range [%d, %d) must be non-empty, inside [0, %d) and aligned to 128", row0, row1, N);
     GDN_CHECK_ARG(ws != nullptr && ws_bytes >= graph_build_ws_bytes(N, D, K), "graph_build: workspace too small");
     const bool tc_ok = gram_tc_supported(N, D, K);
     GDN_CHECK_ARG(use_tc <= 0 || tc_ok,
@@ -214,9 +219,9 @@ int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_
     if (use_tc > 0 || (use_tc < 0 && tc_ok)) {
         float* nrm = nullptr;
         int* flags = nullptr;
-        if (int rc = launch_gram_tc(V, N, D, K, idx, nbr, ws, st, kth, margin, &nrm, &flags)) return rc;
+        if (int rc = launch_gram_tc(V, N, D, K, row0, row1, idx, nbr, ws, st, kth, margin, &nrm, &flags)) return rc;
         // exact fix-up of the (normally zero) 64-row blocks whose candidate window was ambiguous
-        k_gram_topk<<<ceil_div(N, GB_TI), 256, smem, st>>>(V, nrm, N, D, K, idx, nbr, flags, kth);
+        k_gram_topk<<<ceil_div(row1, GB_TI) - row0 / GB_TI, 256, smem, st>>>(V, nrm, N, D, K, row0 / GB_TI, idx, nbr, flags, kth);
         GDN_CHECK_LAUNCH("k_gram_topk_fixup");
         return 0;
     }
@@ -225,7 +230,7 @@ int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_
     if (g > 8 * num_sms()) g = 8 * num_sms();
     k_row_norms<<<g, 256, 0, st>>>(V, N, D, nrm);
     GDN_CHECK_LAUNCH("k_row_norms");
-    k_gram_topk<<<ceil_div(N, GB_TI), 256, smem, st>>>(V, nrm, N, D, K, idx, nbr, nullptr, kth);
+    k_gram_topk<<<ceil_div(row1, GB_TI) - row0 / GB_TI, 256, smem, st>>>(V, nrm, N, D, K, row0 / GB_TI, idx, nbr, nullptr, kth);
     GDN_CHECK_LAUNCH("k_gram_topk");
     return 0;
 }

@@ -64,8 +64,8 @@ int launch_fin_embed(const Shape& s, const float* part, int nrec, double* sums, 
 
 // graph_build.cu
 size_t graph_build_ws_bytes(int N, int D, int K);
-int launch_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr, void* ws, size_t ws_bytes,
-                       int use_tc, float* kth, float margin, cudaStream_t st);
+int launch_graph_build(const float* V, int N, int D, int K, int row0, int row1, int64_t* idx, int32_t* nbr, void* ws,
+                       size_t ws_bytes, int use_tc, float* kth, float margin, cudaStream_t st);
 
 // scoring.cu
 // metrics.cu

@@ -58,11 +58,23 @@ class FlatGradAllReduce:
         return flat
 
 
+def graph_row_shard(n_rows, rank, world, align=128):
+    """Row range of `rank` in the row-sharded graph build (optional exchange step): equal chunks of
+    `chunk` rows, `chunk` a multiple of `align` (the tensor-core engine's row block), the last ones possibly short
+    or empty.  Returns (row0, row1, chunk); row0 == row1 means "nothing to build"."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    per = -(-n_rows // world)
+    chunk = -(-per // align) * align
+    r0 = min(n_rows, rank * chunk)
+    return r0, min(n_rows, r0 + chunk), chunk
+
+
 class WindowShardedTrainer:
     """The reference's train step (train.py:68-73: zero_grad, forward, mse, backward, Adam
     step) on this rank's window shard, with the flat gradient all-reduce before the step."""
 
-    def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None):
+    def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, shard_graph=None):
         self.model = model
         params = list(model.parameters())
         kw = {}
@@ -72,6 +84,13 @@ class WindowShardedTrainer:
             kw["fused"] = True
         self.opt = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, **kw)
         self.reduce = FlatGradAllReduce(params, group)
+        # the graph depends on the (replicated) embedding only: every rank builds 1/world of its rows and the
+        # neighbour tables are all-gathered (the one exchange step of the forward; off for a single process)
+        if shard_graph is None:
+            shard_graph = (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+                           and all(p.is_cuda for p in params) and hasattr(model, "shard_graph_build"))
+        if shard_graph:
+            model.shard_graph_build(dist.get_rank(group), dist.get_world_size(group), group)
 
     def step(self, x, y):
         self.opt.zero_grad(set_to_none=True)

@@ -123,6 +123,7 @@ class GDN(nn.Module):
         self.use_tensor_cores = -1        # graph builder engine: -1 auto, 0 fp32 FMA, 1 tcgen05
         self._kth = None                  # per-row K-th cosine of the last graph build (warm-start hint)
         self.graph_margin = 0.03          # admission slack below that hint
+        self._graph_shard = None          # (rank, world, group): row-sharded graph build + all-gather (data parallel)
 
     def init_params(self):
         nn.init.kaiming_uniform_(self.embedding.weight, a=math.sqrt(5))
@@ -132,6 +133,30 @@ class GDN(nn.Module):
         """Test hook: use this keep mask ([B, N, D], values 0 or 1/(1-p)) instead of Philox for the
         next training forwards (None restores the in-kernel RNG)."""
         self._dropout_mask = mask
+
+    def shard_graph_build(self, rank, world, group=None):
+        """Data-parallel training: the embedding is replicated, so the graph is identical on every rank -- build
+        rows [rank's range) here and all-gather the tables (optional exchange step).  Only TRAINING
+        forwards use it (they run in lock-step on every rank; an eval forward on one rank builds the whole graph
+        locally, so it can never wait for peers).  world <= 1 or `None` switches it off."""
+        self._graph_shard = None if (rank is None or world is None or world <= 1) else (int(rank), int(world), group)
+        self._graph_cache = None
+
+    def _build_graph_sharded(self, w):
+        import torch.distributed as dist
+        from ..dp import graph_row_shard
+        rank, world, group = self._graph_shard
+        N, K = w.shape[0], int(self.topk)
+        r0, r1, chunk = graph_row_shard(N, rank, world)
+        idx = torch.empty((world * chunk, K), dtype=torch.int64, device=w.device)
+        nbr = torch.empty((world * chunk, K + 1), dtype=torch.int32, device=w.device)
+        if r1 > r0:
+            ops.graph_build(w, K, use_tensor_cores=self.use_tensor_cores, kth=self._kth, margin=self.graph_margin,
+                            rows=(r0, r1), out=(idx, nbr))
+        # in-place all-gather: every rank's chunk sits at its own offset of the padded tables
+        dist.all_gather_into_tensor(nbr, nbr[rank * chunk:(rank + 1) * chunk], group=group)
+        dist.all_gather_into_tensor(idx, idx[rank * chunk:(rank + 1) * chunk], group=group)
+        return idx[:N], nbr[:N]
 
     def build_graph(self):
         """models/GDN.py:143-159.  The reference rebuilds the graph in every forward; so do we in
@@ -145,8 +170,12 @@ class GDN(nn.Module):
                 self._kth = torch.full((w.shape[0],), float("-inf"), dtype=torch.float32, device=w.device)
             # warm start: last build's K-th cosine per row (the embedding moves one optimiser step between
             # builds); purely an accelerator -- stale hints are detected and recomputed exactly
-            idx, nbr = ops.graph_build(w, self.topk, use_tensor_cores=self.use_tensor_cores, kth=self._kth,
-                                       margin=self.graph_margin)
+            if self._graph_shard is not None and self.training:
+                # collective: every rank of the group must be in its training forward (eval builds locally)
+                idx, nbr = self._build_graph_sharded(w)
+            else:
+                idx, nbr = ops.graph_build(w, self.topk, use_tensor_cores=self.use_tensor_cores, kth=self._kth,
+                                           margin=self.graph_margin)
             self._graph_cache = None if self.training else (key, idx, nbr)
             return idx, nbr
         return self._graph_cache[1], self._graph_cache[2]

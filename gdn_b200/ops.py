@@ -41,12 +41,15 @@ def make_dims(B, N, W, D, K):
 
 
 # ----------------------------------------------------------------------------- graph
-def graph_build(V, topk, use_tensor_cores=-1, want_idx=True, kth=None, margin=0.03):
+def graph_build(V, topk, use_tensor_cores=-1, want_idx=True, kth=None, margin=0.03, rows=None, out=None):
     """models/GDN.py:143-159 -> (learned_graph [N,K] int64, nbr [N,K+1] int32).
 
     kth: optional float32 [N] CUDA tensor, in/out: the K-th largest cosine of every row from the previous
     build (fill with -inf for "no hint"); warm-starts the tensor-core engine's admission threshold and
-    receives this build's values.  The result never depends on the hint."""
+    receives this build's values.  The result never depends on the hint.
+    rows = (row0, row1): build only those rows (row0 % 128 == 0, row1 % 128 == 0 or row1 == N) -- the
+    row-sharded build of the data-parallel trainer; `out` = (idx, nbr) buffers with at least N rows to write into
+    (rows outside the range are left as they are)."""
     _need_cuda(V, "embedding.weight")
     lib = _lib.load()
     Vc = _f32c(V)
@@ -54,16 +57,28 @@ def graph_build(V, topk, use_tensor_cores=-1, want_idx=True, kth=None, margin=0.
     K = int(topk)
     if not 1 <= K <= N:
         raise RuntimeError(f"topk={K} must be in 1..node_num={N} (torch.topk would raise too)")
-    idx = torch.empty((N, K), dtype=torch.int64, device=Vc.device) if want_idx else None
-    nbr = torch.empty((N, K + 1), dtype=torch.int32, device=Vc.device)
+    if out is not None:
+        idx, nbr = out
+        if idx.dtype != torch.int64 or nbr.dtype != torch.int32 or idx.shape[0] < N or nbr.shape[0] < N \
+                or tuple(idx.shape[1:]) != (K,) or tuple(nbr.shape[1:]) != (K + 1,) \
+                or not idx.is_contiguous() or not nbr.is_contiguous() or idx.device != Vc.device or nbr.device != Vc.device:
+            raise RuntimeError("out must be contiguous (int64 [>=N, K], int32 [>=N, K+1]) on the embedding's device")
+    else:
+        idx = torch.empty((N, K), dtype=torch.int64, device=Vc.device) if want_idx else None
+        nbr = torch.empty((N, K + 1), dtype=torch.int32, device=Vc.device)
     nb = lib.gdn_graph_build_ws_bytes(N, D, K)
     ws = _blob(nb, Vc.device)
-    if kth is None:
+    if kth is not None and (kth.dtype != torch.float32 or kth.device != Vc.device or kth.numel() != N
+                            or not kth.is_contiguous()):
+        raise RuntimeError("kth must be a contiguous float32 [N] tensor on the embedding's device")
+    if rows is not None:
+        r0, r1 = int(rows[0]), int(rows[1])
+        check(lib.gdn_graph_build_rows(ptr(Vc), N, D, K, r0, r1, ptr(idx), ptr(nbr), ptr(ws), ws.numel(),
+                                       int(use_tensor_cores), ptr(kth), float(margin), _stream()), "gdn_graph_build_rows")
+    elif kth is None:
         check(lib.gdn_graph_build(ptr(Vc), N, D, K, ptr(idx), ptr(nbr), ptr(ws), ws.numel(), int(use_tensor_cores),
                                   _stream()), "gdn_graph_build")
     else:
-        if kth.dtype != torch.float32 or kth.device != Vc.device or kth.numel() != N or not kth.is_contiguous():
-            raise RuntimeError("kth must be a contiguous float32 [N] tensor on the embedding's device")
         check(lib.gdn_graph_build_warm(ptr(Vc), N, D, K, ptr(idx), ptr(nbr), ptr(ws), ws.numel(),
                                        int(use_tensor_cores), ptr(kth), float(margin), _stream()),
               "gdn_graph_build_warm")

@@ -140,6 +140,12 @@ int    gdn_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_
 int    gdn_graph_build_warm(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr,
                             void* ws, size_t ws_bytes, int use_tensor_cores, float* kth, float margin,
                             void* stream);
+/* Rows [row0, row1) of the same graph only -- the row-sharded build of the window-sharded data-parallel
+ * trainer (optional exchange step): every rank builds its rows, the neighbour tables
+ * are all-gathered.  row0 must be a multiple of 128, row1 a multiple of 128 or N; idx / nbr are the full
+ * [N, K] / [N, K+1] arrays (only the range is written); kth may be NULL (no warm start). */
+int    gdn_graph_build_rows(const float* V, int N, int D, int K, int row0, int row1, int64_t* idx, int32_t* nbr,
+                            void* ws, size_t ws_bytes, int use_tensor_cores, float* kth, float margin, void* stream);
 
 /* ---- a3/a4: GraphLayer on the window-shared graph ------------------------------------
  * x [B, N, W], V [N, D], nbr [N, K+1] -> out [B*N, D]

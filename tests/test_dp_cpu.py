@@ -89,3 +89,21 @@ def test_single_process_is_a_noop():
     model = _Tiny(3, 2)
     red = FlatGradAllReduce(model.parameters())
     assert red() is None and red.world_size() == 1
+
+
+def test_graph_row_shard_covers_rows_in_aligned_chunks():
+    from gdn_b200.dp import graph_row_shard
+    for n in (1, 127, 128, 1024, 1500, 4096, 16384, 16385):
+        for world in (1, 2, 3, 8):
+            seen, chunk0 = 0, None
+            for r in range(world):
+                r0, r1, chunk = graph_row_shard(n, r, world)
+                chunk0 = chunk if chunk0 is None else chunk0
+                assert chunk == chunk0 and chunk % 128 == 0 and world * chunk >= n
+                assert r0 == min(n, r * chunk) and r0 <= r1 <= n and r0 % 128 == 0 or r0 == n
+                assert r1 == n or r1 % 128 == 0
+                assert r0 == seen or r0 == n                     # contiguous, in rank order
+                seen = max(seen, r1)
+            assert seen == n
+    with pytest.raises(ValueError):
+        graph_row_shard(10, 2, 2)

@@ -438,3 +438,31 @@ def test_ragged_shapes_train_step_against_oracle(shape):
     layer = model.gnn_layers[0]
     assert torch.equal(layer.edge_index_1.cpu(), aux_e["edge_index"])
     assert normwise(layer.att_weight_1.cpu(), aux_e["alpha"]) < TOL
+
+
+@pytest.mark.parametrize("N,D,K,engine", [(1500, 128, 17, 1), (4096, 128, 32, 1), (2048, 64, 64, 1), (700, 64, 9, 0), (4096, 128, 32, 0)],
+                         ids=["tc-ragged", "tc-C4", "tc-d64", "fp32-small", "fp32-C4"])
+def test_row_sharded_graph_build_equals_full_build(N, D, K, engine):
+    """SURVEY §8e optional exchange step: every rank builds an aligned row range; the assembled tables (what the
+    all-gather produces) are bit-identical to the single full build, cold and warm-started, for 2, 3 and 8 ranks."""
+    from gdn_b200 import ops
+    from gdn_b200.dp import graph_row_shard
+    torch.manual_seed(N + K)
+    V = ((torch.rand(N, D, device="cuda") * 2 - 1) / D ** 0.5)
+    full_idx, full_nbr = ops.graph_build(V, K, use_tensor_cores=engine)
+    for world in (2, 3, 8):
+        chunk = graph_row_shard(N, 0, world)[2]
+        idx = torch.full((world * chunk, K), -7, dtype=torch.int64, device="cuda")
+        nbr = torch.full((world * chunk, K + 1), -7, dtype=torch.int32, device="cuda")
+        kth = torch.full((N,), float("-inf"), device="cuda")
+        for rnd in range(2):                                  # second round: warm-started from the first
+            for r in range(world):
+                r0, r1, _ = graph_row_shard(N, r, world)
+                if r1 > r0:
+                    ops.graph_build(V, K, use_tensor_cores=engine, kth=kth, rows=(r0, r1), out=(idx, nbr))
+            assert torch.equal(idx[:N], full_idx) and torch.equal(nbr[:N], full_nbr), (world, rnd)
+        assert bool((idx[N:] == -7).all()) and bool((nbr[N:] == -7).all())      # rows outside every range untouched
+    with pytest.raises(RuntimeError, match="aligned to 128"):
+        ops.graph_build(V, K, use_tensor_cores=engine, rows=(64, N))
+    with pytest.raises(RuntimeError, match="aligned to 128"):
+        ops.graph_build(V, K, use_tensor_cores=engine, rows=(0, 0))
