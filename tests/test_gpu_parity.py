@@ -466,3 +466,37 @@ def test_row_sharded_graph_build_equals_full_build(N, D, K, engine):
         ops.graph_build(V, K, use_tensor_cores=engine, rows=(64, N))
     with pytest.raises(RuntimeError, match="aligned to 128"):
         ops.graph_build(V, K, use_tensor_cores=engine, rows=(0, 0))
+
+
+def test_tensor_core_lin_backward_matches_fma_kernels(tmp_path):
+    """The mma.sync (3xTF32) lin-backward contractions against the FMA kernels they replace (GDN_NO_MMA=3 selects
+    the latter; the switch is read once per process, hence two subprocesses): same loss bit for bit (the forward is
+    untouched) and every gradient within 2e-5 normwise at a C4-sized step, i.e. the FMA kernels' own fp32 noise."""
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "dump.py"
+    script.write_text(
+        "import sys, torch\n"
+        "from gdn_b200.models.GDN import GDN\n"
+        "torch.manual_seed(5)\n"
+        "N, W, D, K, B = 4096, 16, 128, 32, 48\n"
+        "m = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()\n"
+        "m.dp.p = 0.0\n"
+        "x = torch.rand(B, N, W, device='cuda'); y = torch.rand(B, N, device='cuda')\n"
+        "loss = torch.nn.functional.mse_loss(m(x, None), y); loss.backward()\n"
+        "out = {'loss': loss.detach().cpu()}\n"
+        "out.update({k: p.grad.cpu() for k, p in m.named_parameters()})\n"
+        "torch.save(out, sys.argv[1])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mask in ("0", "3"):
+        env = dict(os.environ, GDN_NO_MMA=mask, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        f = tmp_path / f"g{mask}.pt"
+        subprocess.run([sys.executable, str(script), str(f)], check=True, env=env, timeout=300)
+        res[mask] = torch.load(f)
+    assert torch.equal(res["0"]["loss"], res["3"]["loss"])
+    for k, g in res["3"].items():
+        if k == "loss" or k.endswith("gnn.bias"):          # gnn.bias: analytically zero gradient, pure rounding noise
+            continue
+        assert normwise(res["0"][k], g) < 2e-5, (k, normwise(res["0"][k], g))
