@@ -500,13 +500,15 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int row0, 
 #pragma unroll 1
         for (; bit >= 0 && nT > Lmax; bit -= 2) {
             const unsigned c1 = T | (1u << bit), c2 = T | (2u << bit), c3 = T | (3u << bit);
-            unsigned c = 0;                                               // three counts (< 1024 each), 10 bits apiece
+            unsigned c = 0, d = 0;                                        // counts up to S*L (> 1023 possible): 16-bit fields
             for (int e = lane; e < total; e += 32) {
                 const unsigned k = pk[e];
-                c += (k >= c1 ? 1u : 0u) + (k >= c2 ? 1u << 10 : 0u) + (k >= c3 ? 1u << 20 : 0u);
+                c += (k >= c1 ? 1u : 0u) + (k >= c2 ? 1u << 16 : 0u);
+                d += (k >= c3 ? 1u : 0u);
             }
             c = __reduce_add_sync(0xffffffffu, c);
-            const int n1 = c & 1023, n2 = (c >> 10) & 1023, n3 = c >> 20;
+            d = __reduce_add_sync(0xffffffffu, d);
+            const int n1 = c & 0xffff, n2 = c >> 16, n3 = (int)d;
             if (n3 >= L) { T = c3; nT = n3; }
             else if (n2 >= L) { T = c2; nT = n2; }
             else if (n1 >= L) { T = c1; nT = n1; }
@@ -527,13 +529,15 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int row0, 
             const unsigned km = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int slot = kept_before + __popc(km & lt);
-                s_av[wid][slot] = key2f(k);
-                s_j[wid][slot] = pj[e];
+                if (slot < RS_MAXSEL) {                       // (always true: nT <= Lmax <= RS_MAXSEL; belt and braces)
+                    s_av[wid][slot] = key2f(k);
+                    s_j[wid][slot] = pj[e];
+                }
             }
             eq_before += __popc(eqm);
             kept_before += __popc(km);
         }
-        have = kept_before;
+        have = min(kept_before, RS_MAXSEL);
     }
     if (lane == 0 && have < L) block_flags[i / 64] = 1;       // stale warm-start hint: exact fix-up
     __syncwarp();

@@ -440,8 +440,9 @@ def test_ragged_shapes_train_step_against_oracle(shape):
     assert normwise(layer.att_weight_1.cpu(), aux_e["alpha"]) < TOL
 
 
-@pytest.mark.parametrize("N,D,K,engine", [(1500, 128, 17, 1), (4096, 128, 32, 1), (2048, 64, 64, 1), (700, 64, 9, 0), (4096, 128, 32, 0)],
-                         ids=["tc-ragged", "tc-C4", "tc-d64", "fp32-small", "fp32-C4"])
+@pytest.mark.parametrize("N,D,K,engine", [(1500, 128, 17, 1), (4096, 128, 32, 1), (2048, 64, 64, 1), (16384, 128, 64, 1),
+                                          (700, 64, 9, 0), (4096, 128, 32, 0)],
+                         ids=["tc-ragged", "tc-C4", "tc-d64", "tc-C5", "fp32-small", "fp32-C4"])
 def test_row_sharded_graph_build_equals_full_build(N, D, K, engine):
     """SURVEY §8e optional exchange step: every rank builds an aligned row range; the assembled tables (what the
     all-gather produces) are bit-identical to the single full build, cold and warm-started, for 2, 3 and 8 ranks."""
