@@ -12,7 +12,7 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl")
 dev = torch.device("cuda", torch.cuda.current_device())
-for N, W, D, K, B in ((1500, 5, 64, 17, 8), (4096, 16, 128, 32, 16)):
+for N, W, D, K, B in ((1500, 5, 64, 17, 8), (4096, 16, 128, 32, 16), (16384, 16, 128, 64, 4)):
     torch.manual_seed(5)
     model = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).to(dev).train()
     trainer = WindowShardedTrainer(model, lr=1e-3)
