@@ -10,64 +10,53 @@ Two execution paths, both hand-written CUDA behind the C ABI:
 import math
 
 import torch
-import torch.nn.functional as F
 from torch.nn import Linear, Parameter
 
 from gdn_b200 import ops
 
 
-def glorot(tensor):
-    """torch_geometric.nn.inits.glorot (PyG 1.5.0)."""
-    if tensor is not None:
-        stdv = math.sqrt(6.0 / (tensor.size(-2) + tensor.size(-1)))
-        tensor.data.uniform_(-stdv, stdv)
+def _glorot_(t):
+    """PyG 1.5.0 `inits.glorot`: U(-a, a) with a = sqrt(6 / (fan_in + fan_out)) over the last two dims."""
+    if t is None:
+        return
+    bound = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        t.uniform_(-bound, bound)
 
 
-def zeros(tensor):
-    if tensor is not None:
-        tensor.data.fill_(0)
+_ATT_NAMES = ("att_i", "att_j", "att_em_i", "att_em_j")       # state_dict keys of models/graph_layer.py:31-34
 
 
 class GraphLayer(torch.nn.Module):
+    """Constructor arguments as models/graph_layer.py:12-13 (`inter_dim` is accepted and unused there too)."""
+
     def __init__(self, in_channels, out_channels, heads=1, concat=True,
                  negative_slope=0.2, dropout=0, bias=True, inter_dim=-1, **kwargs):
         super().__init__()
         if kwargs.get("aggr", "add") != "add" or kwargs.get("flow", "source_to_target") != "source_to_target":
             raise NotImplementedError("GraphLayer: only aggr='add', flow='source_to_target' (the reference's use)")
         self.aggr, self.flow, self.node_dim = "add", "source_to_target", 0
-
-        self.in_channels = in_channels
-        self.out_channels = out_channels
-        self.heads = heads
-        self.concat = concat
-        self.negative_slope = negative_slope
-        self.dropout = dropout
-
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.concat, self.negative_slope, self.dropout = concat, negative_slope, dropout
         self.__alpha__ = None
-
+        # parameter creation order = the reference's, so that a same-seed construction draws the same numbers
         self.lin = Linear(in_channels, heads * out_channels, bias=False)
-
-        self.att_i = Parameter(torch.Tensor(1, heads, out_channels))
-        self.att_j = Parameter(torch.Tensor(1, heads, out_channels))
-        self.att_em_i = Parameter(torch.Tensor(1, heads, out_channels))
-        self.att_em_j = Parameter(torch.Tensor(1, heads, out_channels))
-
-        if bias and concat:
-            self.bias = Parameter(torch.Tensor(heads * out_channels))
-        elif bias and not concat:
-            self.bias = Parameter(torch.Tensor(out_channels))
+        for name in _ATT_NAMES:
+            setattr(self, name, Parameter(torch.empty(1, heads, out_channels)))
+        if bias:
+            self.bias = Parameter(torch.empty(heads * out_channels if concat else out_channels))
         else:
-            self.register_parameter('bias', None)
-
+            self.register_parameter("bias", None)
         self.reset_parameters()
 
     def reset_parameters(self):
-        glorot(self.lin.weight)
-        glorot(self.att_i)
-        glorot(self.att_j)
-        zeros(self.att_em_i)
-        zeros(self.att_em_j)
-        zeros(self.bias)
+        """models/graph_layer.py:42-49: glorot for lin / att_i / att_j (in this order), zeros for the rest."""
+        for t in (self.lin.weight, self.att_i, self.att_j):
+            _glorot_(t)
+        with torch.no_grad():
+            for t in (self.att_em_i, self.att_em_j, self.bias):
+                if t is not None:
+                    t.zero_()
 
     # ------------------------------------------------------------------ reference signature
     def forward(self, x, edge_index, embedding, return_attention_weights=False):
@@ -108,5 +97,4 @@ class GraphLayer(torch.nn.Module):
         return (out, alpha) if return_attention_weights else out
 
     def __repr__(self):
-        return '{}({}, {}, heads={})'.format(self.__class__.__name__, self.in_channels,
-                                             self.out_channels, self.heads)
+        return f"{type(self).__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})"
