@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgdn_b200.so")
-SOURCES = ["api.cu", "attention.cu", "dwide.cu", "graph_build.cu", "scoring.cu", "csr.cu", "windows.cu", "metrics.cu"]
+SOURCES = ["api.cu", "attention.cu", "dwide.cu", "graph_build.cu", "scoring.cu", "csr.cu", "windows.cu", "metrics.cu", "optim.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]

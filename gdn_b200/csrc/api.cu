@@ -441,6 +441,17 @@ int gdn_score(const float* pred, const float* gt, int T, int N, double* scores, 
     return launch_score(pred, gt, T, N, scores, top1, stats, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------- optimiser
+int gdn_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale, void* stream) {
+    GDN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n >= 1, "adam_flat: bad argument");
+    GDN_CHECK_ARG(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && lr >= 0.f,
+                  "adam_flat: bad hyper-parameters (step=%lld)", step);
+    prof_enter((cudaStream_t)stream, "@adam_flat");
+    return launch_adam_flat(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                            (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------- metrics
 int gdn_f1_sweep(const double* sorted_scores, const float* labels_sorted, int T, const int* k_pred, const int* k_thr,
                  int S, double* fmeas, double* thresholds, void* stream) {

@@ -68,6 +68,10 @@ int launch_graph_build(const float* V, int N, int D, int K, int row0, int row1, 
                        size_t ws_bytes, int use_tc, float* kth, float margin, cudaStream_t st);
 
 // scoring.cu
+// optim.cu
+int launch_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, long long step, float grad_scale, cudaStream_t st);
+
 // metrics.cu
 int launch_f1_sweep(const double* sorted_scores, const float* labels_sorted, int T, const int* k_pred, const int* k_thr,
                     int S, double* fmeas, double* thresholds, cudaStream_t st);

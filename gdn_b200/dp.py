@@ -74,16 +74,27 @@ class WindowShardedTrainer:
     """The reference's train step (train.py:68-73: zero_grad, forward, mse, backward, Adam
     step) on this rank's window shard, with the flat gradient all-reduce before the step."""
 
-    def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, shard_graph=None):
+    def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, shard_graph=None, flat_adam=False):
+        """flat_adam=True: parameters, gradients and Adam moments live in flat buffers
+        (`gdn_b200.optim.FlatAdam`); the all-reduce works on the gradient buffer in place and the 1/world scaling is
+        fused into the single Adam kernel.  Default: torch.optim.Adam (fused on CUDA) + FlatGradAllReduce."""
         self.model = model
+        self.group = group
         params = list(model.parameters())
-        kw = {}
-        if fused_adam is None:
-            fused_adam = all(p.is_cuda for p in params)
-        if fused_adam:
-            kw["fused"] = True
-        self.opt = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, **kw)
-        self.reduce = FlatGradAllReduce(params, group)
+        self.flat = None
+        if flat_adam:
+            from .optim import FlatAdam
+            self.flat = FlatAdam(params, lr=lr, weight_decay=weight_decay)
+            self.opt = self.flat
+            self.reduce = None
+        else:
+            kw = {}
+            if fused_adam is None:
+                fused_adam = all(p.is_cuda for p in params)
+            if fused_adam:
+                kw["fused"] = True
+            self.opt = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, **kw)
+            self.reduce = FlatGradAllReduce(params, group)
         # the graph depends on the (replicated) embedding only: every rank builds 1/world of its rows and the
         # neighbour tables are all-gathered (the one exchange step of the forward; off for a single process)
         if shard_graph is None:
@@ -93,6 +104,18 @@ class WindowShardedTrainer:
             model.shard_graph_build(dist.get_rank(group), dist.get_world_size(group), group)
 
     def step(self, x, y):
+        if self.flat is not None:
+            self.flat.zero_grad()
+            out = self.model(x, None)
+            loss = torch.nn.functional.mse_loss(out, y, reduction="mean")
+            loss.backward()
+            world = 1
+            if dist.is_available() and dist.is_initialized():
+                world = dist.get_world_size(self.group)
+                if world > 1:
+                    dist.all_reduce(self.flat.grad_buffer, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.step(grad_scale=1.0 / world)
+            return loss
         self.opt.zero_grad(set_to_none=True)
         out = self.model(x, None)
         loss = torch.nn.functional.mse_loss(out, y, reduction="mean")

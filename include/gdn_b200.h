@@ -17,6 +17,7 @@
  *   gdn_f1_sweep, gdn_binary_counts, gdn_auc_ranksum
  *                          util/data.py:28-51 (eval_scores) and evaluate.py:129-158
  *                          (get_best_performance_data): threshold sweep / F1, precision, recall, AUC
+ *   gdn_adam_flat          train.py:31,73 (torch.optim.Adam step) on flat buffers, 1/G gradient scaling fused
  *   gdn_window_batch       datasets/TimeDataset.py:33-62 (+ the per-step transfer train.py:66):
  *                          window batches gathered from a device-resident series
  *
@@ -202,6 +203,13 @@ int    gdn_ctx_alpha(const gdn_dims* d, const int32_t* nbr, const void* ctx, flo
 size_t gdn_score_ws_bytes(int T, int N);
 int    gdn_score(const float* pred, const float* gt, int T, int N, double* scores, double* top1,
                  double* stats, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- optimiser (train.py:31, 73) ----
+ * torch.optim.Adam (amsgrad off) on flat float32 buffers of n elements: grads are multiplied by grad_scale first
+ * (1/world_size after a sum all-reduce), weight_decay is the L2 form (grad += wd * param), step counts from 1. */
+int    gdn_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale,
+                     void* stream);
 
 /* ---- evaluation metrics (util/data.py:28-51, evaluate.py:129-158) ----
  * sorted_scores [T] float64 ascending (stable), labels_sorted [T] float32 in {0,1} in the same order.

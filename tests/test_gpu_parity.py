@@ -501,3 +501,50 @@ def test_tensor_core_lin_backward_matches_fma_kernels(tmp_path):
         if k == "loss" or k.endswith("gnn.bias"):          # gnn.bias: analytically zero gradient, pure rounding noise
             continue
         assert normwise(res["0"][k], g) < 2e-5, (k, normwise(res["0"][k], g))
+
+
+def test_flat_adam_matches_torch_adam_and_trains_identically():
+    """gdn_adam_flat on flat buffers == torch.optim.Adam (train.py:31,73) on random gradients
+    over several steps (with and without weight decay, with a gradient scale), and a model trained through
+    WindowShardedTrainer(flat_adam=True) follows the default trainer's loss curve and weights."""
+    from gdn_b200.dp import WindowShardedTrainer
+    from gdn_b200.models.GDN import GDN
+    from gdn_b200.optim import FlatAdam
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for wd, scale in ((0.0, 1.0), (0.01, 0.25)):
+        shapes = [(7, 5), (33,), (1, 1, 64), (129, 16)]
+        a = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+        b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+        ref = torch.optim.Adam(a, lr=3e-3, weight_decay=wd)
+        ours = FlatAdam(b, lr=3e-3, weight_decay=wd)
+        for step in range(6):
+            grads = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+            ours.zero_grad()
+            for p, q, gr in zip(a, b, grads):
+                p.grad = gr * scale
+                q.grad += gr                                   # accumulates into the flat buffer's view
+            ref.step()
+            ours.step(grad_scale=scale)
+            for p, q in zip(a, b):
+                assert normwise(q.detach().cpu(), p.detach().cpu()) < 2e-6, (wd, step)
+        assert all(q.data_ptr() >= ours.flat.data_ptr() for q in b) and ours.step_count == 6
+    # whole train steps: same seeds, same batches
+    N, W, D, K, B = 70, 7, 64, 9, 16
+    xs = [torch.rand(B, N, W, device="cuda", generator=g) for _ in range(5)]
+    ys = [torch.rand(B, N, device="cuda", generator=g) for _ in range(5)]
+
+    def run(flat):
+        torch.manual_seed(2)
+        m = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()
+        m.dp.p = 0.0
+        tr = WindowShardedTrainer(m, lr=1e-3, flat_adam=flat)
+        return [tr.step(x, y).item() for x, y in zip(xs, ys)], m
+
+    la, ma = run(False)
+    lb, mb = run(True)
+    assert all(abs(p - q) <= 2e-5 * abs(p) for p, q in zip(la, lb)), (la, lb)
+    for (k, p), (_, q) in zip(ma.state_dict().items(), mb.state_dict().items()):
+        if k.endswith("gnn.bias"):                             # analytically zero gradient: Adam amplifies rounding noise
+            continue
+        assert normwise(q.float().cpu(), p.float().cpu()) < (5e-2 if "running_mean" in k else 2e-3), k
+    assert set(mb.state_dict().keys()) == set(ma.state_dict().keys())
