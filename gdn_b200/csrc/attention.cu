@@ -57,7 +57,7 @@ __global__ void k_node_scalars(const float* __restrict__ V, const float* __restr
 // A lane's 16 gathers of one neighbour are then base + w*32: immediate offsets, no address math.
 // ---------------------------------------------------------------------------------------
 __global__ void k_transpose_scalars(const float* __restrict__ x, const float* __restrict__ uv,
-                                    const float* __restrict__ ev, int B, int N, int W, int WP, int Bs,
+                                    const float* __restrict__ ev, int B, int N, int W, int WP, int Bs, int vec4,
                                     float* __restrict__ xT, float* __restrict__ siT, float* __restrict__ sjT) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -71,12 +71,30 @@ __global__ void k_transpose_scalars(const float* __restrict__ x, const float* __
         const bool ok = b < B;
         const float* row = x + ((size_t)b * N + i) * W;
         float* dst = xT + ((size_t)i * chunks + c) * WP * 32 + lane;
-        for (int w = 0; w < WP; ++w) {
-            const float v = (ok && w < W) ? __ldg(row + w) : 0.f;
-            dst[w * 32] = v;
-            if (w < W) {
-                si = fmaf(v, uv[w], si);
-                sj = fmaf(v, uv[32 + w], sj);
+        if (vec4) {
+            // 16-byte loads (W % 4 == 0 and x 16-byte aligned): a lane's row is W contiguous floats, rows of different lanes are N*W apart, so the
+            // number of L1 requests (each touching 32 lines) is what bounds this kernel
+            for (int w = 0; w < WP; w += 4) {
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok && w < W) q = __ldg(reinterpret_cast<const float4*>(row + w));
+                const float v4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    dst[(w + u) * 32] = v4[u];
+                    if (w + u < W) {
+                        si = fmaf(v4[u], uv[w + u], si);
+                        sj = fmaf(v4[u], uv[32 + w + u], sj);
+                    }
+                }
+            }
+        } else {
+            for (int w = 0; w < WP; ++w) {
+                const float v = (ok && w < W) ? __ldg(row + w) : 0.f;
+                dst[w * 32] = v;
+                if (w < W) {
+                    si = fmaf(v, uv[w], si);
+                    sj = fmaf(v, uv[32 + w], sj);
+                }
             }
         }
         siT[(size_t)i * Bs + b] = ok ? si + ev[i] : 0.f;
@@ -345,7 +363,8 @@ int launch_prep(const Shape& s, const float* x, const float* V, const gdn_layer_
     GDN_CHECK_LAUNCH("k_node_scalars");
     const long long tasks = (long long)s.N * (s.Bs / 32);
     k_transpose_scalars<<<grid_for_warps(tasks, 8, 16 * num_sms()), 256, 0, st>>>(
-        x, uv, ev, s.B, s.N, s.W, s.WP, s.Bs, (float*)(ctx + L.xT), (float*)(ctx + L.siT), (float*)(ctx + L.sjT));
+        x, uv, ev, s.B, s.N, s.W, s.WP, s.Bs, ((s.W & 3) == 0 && ((uintptr_t)x & 15) == 0) ? 1 : 0, (float*)(ctx + L.xT),
+        (float*)(ctx + L.siT), (float*)(ctx + L.sjT));
     GDN_CHECK_LAUNCH("k_transpose_scalars");
     return 0;
 }
