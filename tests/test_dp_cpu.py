@@ -107,3 +107,62 @@ def test_graph_row_shard_covers_rows_in_aligned_chunks():
             assert seen == n
     with pytest.raises(ValueError):
         graph_row_shard(10, 2, 2)
+
+
+def _cpu_graph_rows(V, topk, use_tensor_cores=-1, want_idx=True, kth=None, margin=0.03, rows=None, out=None):
+    """Stand-in for ops.graph_build (CUDA only) with the same contract, in torch on the CPU: rows [r0, r1) of the
+    cosine top-k and the neighbour table (top-k without self, then self) written into `out`."""
+    N, K = V.shape[0], int(topk)
+    Vn = V / V.norm(dim=1, keepdim=True)
+    r0, r1 = rows if rows is not None else (0, N)
+    idx = torch.topk(Vn[r0:r1] @ Vn.t(), K, dim=1).indices
+    nbr = torch.full((r1 - r0, K + 1), -1, dtype=torch.int32)
+    for a in range(r1 - r0):
+        keep = [int(j) for j in idx[a] if int(j) != r0 + a] + [r0 + a]
+        nbr[a, :len(keep)] = torch.tensor(keep, dtype=torch.int32)
+    full_idx, full_nbr = out
+    full_idx[r0:r1] = idx
+    full_nbr[r0:r1] = nbr
+    return full_idx, full_nbr
+
+
+def _graph_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gdn_b200 import ops
+        from gdn_b200.models.GDN import GDN
+        ops.graph_build = _cpu_graph_rows                      # the kernels are covered by the -m gpu tests
+        torch.manual_seed(3)
+        N, K = 300, 7                                           # 300 rows -> chunks of 256: rank 1 builds only 44 rows
+        model = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=16, input_dim=4, topk=K).train()
+        model.shard_graph_build(rank, world)
+        idx, nbr = model.build_graph()
+        assert idx.shape == (N, K) and nbr.shape == (N, K + 1)
+        full = (torch.empty(N, K, dtype=torch.int64), torch.empty(N, K + 1, dtype=torch.int32))
+        _cpu_graph_rows(model.embedding.weight.detach(), K, out=full)
+        assert torch.equal(idx, full[0]) and torch.equal(nbr, full[1])
+        model.eval()                                            # eval forwards build locally: no collective
+        if rank == 0:
+            called = []
+            ops.graph_build = lambda *a, **k: called.append(k.get("rows")) or _cpu_graph_rows(
+                a[0], a[1], out=(torch.empty(N, K, dtype=torch.int64), torch.empty(N, K + 1, dtype=torch.int32)))
+            idx_e, _ = model.build_graph()
+            assert called == [None] and torch.equal(idx_e, full[0])
+        model.shard_graph_build(None, None)
+        assert model._graph_shard is None
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_graph_build_world2_gloo():
+    """The data-parallel graph exchange on CPU (gloo, world 2): each rank fills its aligned row range, the in-place
+    all-gather assembles the padded tables, the slices equal a full build; an eval forward on one rank needs no peer."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_graph_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert len(ret) == world
