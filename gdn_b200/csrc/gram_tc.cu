@@ -263,14 +263,15 @@ k_gram_tc(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUt
         }
     } else if (warp >= 4) {
         // ===== epilogue: thread <-> row =====
-        // Selection of the best L entries of every row, thread <-> row for the streaming part:
-        //   * a thread appends every value above its row's threshold to the row's buffer (capacity
-        //     C = 2L, global memory, L2-resident; the append is two fire-and-forget stores);
-        //   * when a buffer could overflow within the next 16 columns the warp compacts it
-        //     cooperatively: rank every entry (value desc, position asc), keep ranks < L at slot =
-        //     rank, and raise the threshold to the L-th value.  The threshold is only refreshed at
-        //     compactions, so a row is compacted ~1 + ln(N / 2L) times per sweep instead of paying a
-        //     minimum search per admitted element.
+        // Candidate selection, thread <-> row for the streaming part:
+        //   * a thread appends every value above its row's threshold to the row's segment buffer (capacity
+        //     C = 256 entries, global memory, L2-resident; the append is two fire-and-forget stores);
+        //   * when a buffer could overflow within the next tile (128 columns) the warp compacts it
+        //     cooperatively: the L-th largest key by bit-bisection, keep the L best at slots 0..L-1, and raise
+        //     the threshold to the L-th value.  The threshold is only refreshed at compactions, so a cold row is
+        //     compacted ~1 + ln(N / C) times per sweep instead of paying a minimum search per admitted element;
+        //     a warm-started row normally never compacts before the final pass.
+        //   * the row's segments (one per column split and warpgroup) are merged by k_rescore.
         const int wg = (warp - 4) >> 2;              // epilogue warpgroup = TMEM accumulator buffer it drains
         const int seg = 2 * (int)blockIdx.y + wg;    // candidate segment of this (column split, warpgroup)
         const int wrow0 = (warp & 3) * 32;           // first row of this warp inside the CTA (= its TMEM lanes)
