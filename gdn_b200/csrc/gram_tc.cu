@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32)
 k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int row0, int row1, int K, int L, int C, int S,
           const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const int* __restrict__ rowcnt,
           float* __restrict__ kth_out,
-          int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, int* __restrict__ block_flags) {
+          int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, int* __restrict__ block_flags,
+          const int* __restrict__ tc_err) {
     __shared__ unsigned long long s_key[RS_WARPS][RS_MAXSEL];  // ranking keys (exact cosine, index)
     __shared__ float s_av[RS_WARPS][RS_MAXSEL];             // approximate (tensor-core) values of the selection
     __shared__ int s_j[RS_WARPS][RS_MAXSEL];
@@ -451,6 +452,9 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int row0, 
     const int li = blockIdx.x * RS_WARPS + wid;               // row inside the range = row of the candidate buffers
     const int i = row0 + li;
     if (i >= row1) return;
+    // a pipeline protocol error in k_gram_tc (bounded mbarrier wait expired; never observed) leaves candidate
+    // lists incomplete: hand every block to the exact engine instead of trusting them
+    if (*tc_err != 0 && lane == 0) block_flags[i / 64] = 1;
     constexpr int TS = D + 4;                                    // tile row stride: conflict-free float4 row reads
     float* tile = rs_smem + (size_t)wid * (32 * TS + D);
     float* svi = tile + 32 * TS;
@@ -740,7 +744,7 @@ int launch_gram_tc(const float* V, int N, int D, int K, int row0, int row1, int6
     e = ensure_dyn_smem_ptr(reinterpret_cast<const void*>(rescore), rs_smem);
     if (e != cudaSuccess) return cuda_fail(e, "smem attr k_rescore");
     rescore<<<ceil_div(row1 - row0, RS_WARPS), RS_WARPS * 32, rs_smem, st>>>(V, nrm, row0, row1, K, L, C, S, bufv, bufj, rowcnt,
-                                                                            kth, idx, nbr, flags);
+                                                                            kth, idx, nbr, flags, err);
     GDN_CHECK_LAUNCH("k_rescore");
     *nrm_out = nrm;
     *flags_out = flags;
