@@ -51,3 +51,32 @@ def test_test_loop_oracle_equals_reference():
     N, T, W = (int(v) for v in rec["dims"][:3])
     _, y, lab = do.process(rec["raw"].tolist(), W, 1, "test")
     assert np.array_equal(gt, y.astype(np.float32)) and np.array_equal(labels[:, 0], lab.astype(np.float32))
+
+
+def test_host_mirrors_fail_loudly_without_cuda():
+    """No CPU fallback anywhere on the widened rows either (f-2, f-3, f-4): the mirrors raise instead of computing."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    from gdn_b200.evaluate import get_best_performance_data
+    from gdn_b200.optim import FlatAdam
+    from gdn_b200.test import test as run_test
+    from gdn_b200.util.data import eval_scores
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        run_test(torch.nn.Linear(2, 2), [])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        eval_scores([0.1, 0.2], [0, 1], 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        get_best_performance_data([[0.1, 0.2]], [0, 1])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        FlatAdam([torch.nn.Parameter(torch.zeros(3))])
+
+
+def test_test_result_is_indexable_like_the_reference_lists():
+    import torch
+    from gdn_b200.test import TestResult
+    p, g, l = torch.rand(5, 3), torch.rand(5, 3), torch.zeros(5, 3)
+    res = TestResult(p, g, l)
+    assert len(res) == 3 and torch.equal(res[0], p) and res.device_tensors[1] is g
+    assert np.asarray(res).shape == (3, 5, 3)                                  # main.py:get_score does np.array(test_result)
+    assert np.array_equal(np.asarray(res)[2, :, 0], np.zeros(5))
