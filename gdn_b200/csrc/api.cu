@@ -1,6 +1,8 @@
 // api.cu -- extern "C" entry points of libgdn_b200.so (see include/gdn_b200.h).
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include "common.cuh"
 #include "launchers.h"
 
@@ -52,17 +54,24 @@ void prof_mark(const char* what) {
 }
 
 cudaError_t ensure_dyn_smem_ptr(const void* kernel, size_t bytes) {
-    // per-kernel high-water mark (keyed by the function pointer, NOT by its type: template
-    // instantiations share a type)
-    static const void* keys[512];
-    static size_t have[512];
+    // high-water mark per (device, kernel): cudaFuncSetAttribute is per device/context, and template
+    // instantiations share a type, hence the function pointer as key.  Guarded: several host threads (one per
+    // GPU in a multi-device process) may launch concurrently.
+    static std::mutex mu;
+    static const void* keys[1024];
+    static int devs[1024];
+    static size_t have[1024];
     static int n = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    std::lock_guard<std::mutex> lock(mu);
     int k = 0;
     for (; k < n; ++k)
-        if (keys[k] == kernel) break;
+        if (keys[k] == kernel && devs[k] == dev) break;
     if (k == n) {
-        if (n == 512) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (n == 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         keys[n] = kernel;
+        devs[n] = dev;
         have[n] = 0;   // static + dynamic may already exceed the 48 KB default: always opt in once
         ++n;
     }
@@ -73,16 +82,16 @@ cudaError_t ensure_dyn_smem_ptr(const void* kernel, size_t bytes) {
 }
 
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+    static std::atomic<int> cached[64];            // per device ordinal; 0 = not queried yet
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        int n = 0;
+        v = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+        cached[dev].store(v, std::memory_order_relaxed);
     }
-    return cached;
+    return v;
 }
 
 int make_shape(const gdn_dims* d, Shape* s, bool need_dwide) {

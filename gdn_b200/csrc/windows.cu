@@ -21,8 +21,12 @@ k_window_batch(const float* __restrict__ series, const float* __restrict__ label
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(r / N), i = (int)(r % N);
         const int e = win_end[b];
-        if (e < W || e >= T) {                       // window [e-W, e] must lie inside the series
-            if (i == 0) atomicExch(err, b + 1);
+        if (e < W || e >= T) {                       // window [e-W, e] must lie inside the series: flag it and
+            if (i == 0) atomicExch(err, b + 1);      // hand zeros (never uninitialised memory) to the model
+            float* z = x + (size_t)r * W;
+            for (int w = 0; w < W; ++w) z[w] = 0.f;
+            y[r] = 0.f;
+            if (i == 0 && lab != nullptr) lab[b] = 0.f;
             continue;
         }
         const float* src = series + (size_t)i * T + (e - W);

@@ -26,6 +26,7 @@ class Prefetcher:
         self.stream = torch.cuda.Stream(device=self.device)
         self._pinned = {}
         self._devbuf = {}
+        self._copied = {}        # slot -> event after the slot's last H2D copies (guards the pinned staging buffers)
 
     def __len__(self):
         return len(self.batches)
@@ -43,6 +44,12 @@ class Prefetcher:
         if buf is None:
             buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             self._pinned[key] = buf
+        else:
+            # the slot's previous H2D copy out of this buffer is only stream-ordered; a consumer without a
+            # per-step host sync lets the host run ahead, so wait for that copy HERE before overwriting its source
+            ev = self._copied.get(slot)
+            if ev is not None:
+                ev.synchronize()
         buf.copy_(t)
         return buf
 
@@ -73,6 +80,7 @@ class Prefetcher:
                     out.append(self._to_device(slot, pos, self._stage(slot, pos, t)))
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self._copied[slot] = ev
         return out, ev
 
     def __iter__(self):

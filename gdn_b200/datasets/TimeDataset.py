@@ -82,10 +82,28 @@ class TimeDataset:
         if not _validated and (int(idx.min()) < 0 or int(idx.max()) >= len(self)):
             raise IndexError("window index out of range")
         ends = self.win_end[idx].contiguous()
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        err = self._err_flag()
         check(lib.gdn_window_batch(ptr(self.series), ptr(self.label_series), N, self.total_time_len, W, ptr(ends), B,
                                    ptr(x), ptr(y), ptr(lab), ptr(err), _stream()), "gdn_window_batch")
         return x, y, lab
+
+    def _err_flag(self):
+        """One persistent device flag per dataset (no memset per batch): the kernel stores b+1 there when window b
+        of a batch lies outside the series (and hands zeros to the model); `check_errors` reads it."""
+        flag = getattr(self, "_err", None)
+        if flag is None or flag.device != self.series.device:
+            flag = torch.zeros(1, dtype=torch.int32, device=self.series.device)
+            self._err = flag
+        return flag
+
+    def check_errors(self):
+        """Host-synchronising check of the kernel's error flag (the loader calls it once per epoch)."""
+        flag = getattr(self, "_err", None)
+        if flag is not None:
+            bad = int(flag.item())
+            if bad:
+                flag.zero_()
+                raise IndexError(f"gdn_window_batch: window {bad - 1} of a batch lies outside the series")
 
     def __getitem__(self, idx):
         """Reference item: (feature [N,W], y [N], label, edge_index) as doubles (datasets/TimeDataset.py:64-73).
@@ -131,3 +149,4 @@ class WindowLoader:
             sel = order[k * self.batch_size:(k + 1) * self.batch_size]
             x, y, lab = self.dataset.batch(sel, _validated=True)
             yield x, y, lab, self.dataset.edge_index
+        self.dataset.check_errors()

@@ -65,4 +65,7 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.graph.replay()
+        # the replay moves embedding.weight on the device without touching its version counter: an eval-mode
+        # graph cached before this step (GDN.build_graph keys on data_ptr + _version) is stale now
+        self.model._graph_cache = None
         return self.loss

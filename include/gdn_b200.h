@@ -123,7 +123,13 @@ int gdn_profile_enable(int on);
 int gdn_profile_collect(char* buf, size_t buf_bytes);
 
 /* ---- a1: learned graph (models/GDN.py:143-159) ---------------------------------------
- * V [N, D] -> idx [N, K] int64 (torch.topk order: descending cosine, ties -> lower index)
+ * V [N, D] -> idx [N, K] int64, descending cosine; EXACTLY equal cosines rank the lower column
+ *          first.  That is a deterministic rule of ours, NOT torch.topk's: the reference's
+ *          tie order is an artefact of libstdc++'s partial_sort/nth_element (SURVEY.md
+ *          section 7.1).  Rows whose top-(K+1) reference cosines are > 1e-6 apart equal
+ *          torch.topk bit for bit; tie-affected rows are equal after canonicalising inside
+ *          tau-clusters (oracle/topk_protocol.py, counts asserted in tests/ and recorded
+ *          by bench.py);
  *          and nbr [N, K+1] int32: the neighbour list GraphLayer actually uses after
  *          remove_self_loops/add_self_loops (models/graph_layer.py:61-63): the non-self
  *          top-k entries in order, then the sensor itself, then -1 padding.

@@ -199,16 +199,25 @@ def dropout_mask(batch_num, node_num, dim, seed, p=DROP_P, dtype=torch.float32):
     return m.contiguous().to(dtype)
 
 
-def gdn_forward(sd, data, topk, training=False, drop_mask=None, update_buffers=True):
+def gdn_forward(sd, data, topk, training=False, drop_mask=None, update_buffers=True, idx=None):
     """models/GDN.py:122-187.  ``sd`` holds parameters *and* BN buffers (buffers are
     updated in place in training mode, as nn.BatchNorm1d does).  ``drop_mask`` [B,N,D]
     in {0, 1/(1-p)} replaces nn.Dropout's RNG (required when training).
+    ``idx`` [N, K] int64, optional: use this learned graph instead of computing it (the graph is
+    built without gradient, models/GDN.py:145, so everything downstream is a function of it) --
+    lets a test compare the float path on the graph under test when near-tied cosines make two
+    exact-arithmetic builds differ in a few rows.
     Returns (pred [B, N], aux dict)."""
     x = data.clone().detach()
     B, N, W = x.shape
     x = x.view(-1, W).contiguous()
     V = sd["embedding.weight"]
-    idx, _ = learned_graph(V, topk)                                # :143-159
+    if idx is None:
+        idx, _ = learned_graph(V, topk)                            # :143-159
+    else:
+        idx = torch.as_tensor(idx).long()
+        if tuple(idx.shape) != (N, topk):
+            raise ValueError(f"idx must be [N, K] = {(N, topk)}, got {tuple(idx.shape)}")
     edges = batch_edges(idx, B)                                    # :161-165
     emb_rep = V.repeat(B, 1)                                       # :146
     z, (ei, alpha) = graph_layer_forward(
@@ -254,7 +263,7 @@ def mse_loss(pred, y):
     return F.mse_loss(pred, y, reduction="mean")
 
 
-def loss_and_grads(sd, data, y, topk, drop_mask=None, training=True, update_buffers=False):
+def loss_and_grads(sd, data, y, topk, drop_mask=None, training=True, update_buffers=False, idx=None):
     """One forward + backward (train.py:69-72) -> (loss, pred, {param: grad})."""
     names = param_names(sd)
     work = dict(sd)
@@ -263,7 +272,7 @@ def loss_and_grads(sd, data, y, topk, drop_mask=None, training=True, update_buff
         leaves[k] = sd[k].detach().clone().requires_grad_(True)
         work[k] = leaves[k]
     pred, aux = gdn_forward(work, data, topk, training=training, drop_mask=drop_mask,
-                            update_buffers=update_buffers)
+                            update_buffers=update_buffers, idx=idx)
     if update_buffers:
         for k in sd:
             if k not in leaves:

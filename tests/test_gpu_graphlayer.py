@@ -38,8 +38,8 @@ def test_general_edge_list_matches_reference(heads):
 
 
 @pytest.mark.parametrize("shape", [(27, 5, 64, 5, 32), (51, 5, 64, 15, 40), (96, 16, 128, 12, 7), (33, 10, 32, 7, 5),
-                                   (300, 16, 128, 32, 64)],
-                         ids=["C1", "C2-B40", "w16", "w10", "n300"])
+                                   (300, 16, 128, 32, 64), (4096, 16, 128, 32, 8), (16384, 16, 128, 64, 1)],
+                         ids=["C1", "C2-B40", "w16", "w10", "n300", "C4-B8", "C5-B1"])
 def test_batched_layer_matches_oracle(shape):
     """forward_batched (the hot path) vs the edge-list oracle, incl. all parameter gradients and
     the embedding gradient; the oracle runs in float64 for the gradient reference."""
@@ -54,18 +54,26 @@ def test_batched_layer_matches_oracle(shape):
     gout = torch.randn(B * N, D, generator=g)
     V = sd["embedding.weight"].clone()
     Vc = V.cuda().requires_grad_(True)
-    idx, nbr = ops.graph_build(Vc.detach(), K, use_tensor_cores=0)
+    idx, nbr = ops.graph_build(Vc.detach(), K, use_tensor_cores=0 if N <= 300 else -1)
     out, alpha_ell = layer.forward_batched(x.cuda(), nbr, Vc, return_attention_weights=True)
     out.backward(gout.cuda())
-    # oracle in float64 on the same graph
-    idx_o, _ = go.learned_graph(V, K)
-    assert torch.equal(idx.cpu(), idx_o)
+    # oracle in float64 on the same graph (at the BASELINE scale shapes near-tied cosines may rank differently
+    # in the two builds -- tests/test_gpu_parity.py checks the graph itself by the top-k protocol -- so the
+    # layer is compared on the graph it was given)
+    if N <= 300:
+        idx_o, _ = go.learned_graph(V, K)
+        assert torch.equal(idx.cpu(), idx_o)
+    else:
+        idx_o = idx.cpu()
     edges = go.batch_edges(idx_o, B)
     P = {k: v.double().requires_grad_(True) for k, v in lsd.items()}
     V64 = V.double().requires_grad_(True)
     o64, (ei, a64) = go.graph_layer_forward(x.view(-1, W).double(), edges, V64.repeat(B, 1), P["lin.weight"],
                                             P["att_i"], P["att_j"], P["att_em_i"], P["att_em_j"], P["bias"])
     o64.backward(gout.double())
+    print(f"\nGraphLayer N={N} B={B}: out err {normwise(out.detach().cpu(), o64.detach()):.3e}, "
+          f"g_V err {normwise(Vc.grad.cpu(), V64.grad):.3e}, "
+          + ", ".join(f"{k} {normwise(p.grad.cpu(), P[k].grad):.3e}" for k, p in layer.named_parameters()))
     assert normwise(out.detach().cpu(), o64.detach()) < TOL
     ei2, alpha = ops.reference_edge_layout(nbr, alpha_ell, B)
     assert torch.equal(ei2.cpu(), ei)
