@@ -235,7 +235,8 @@ int    gdn_auc_ranksum(const double* sorted_scores, const float* labels_sorted, 
  * series [N, T] float32 and labels [T] float32 (or NULL) stay resident on the device; a batch is B
  * window-end indices win_end[b] in [W, T):  x[b,i,w] = series[i, win_end[b]-W+w],  y[b,i] = series[i, win_end[b]],
  * lab[b] = labels[win_end[b]] (lab may be NULL).  err: one int, zero-initialised by the caller; receives
- * 1 + b of an out-of-range window (the batch rows of that window are left untouched). */
+ * 1 + b of an out-of-range window (the batch rows of that window are set to zero; the flag is sticky until the
+ * caller clears it, so it can be checked once per epoch instead of once per batch). */
 int    gdn_window_batch(const float* series, const float* labels, int N, int T, int W, const int* win_end, int B,
                         float* x, float* y, float* lab, int* err, void* stream);
 

@@ -78,7 +78,9 @@ def test_edges_and_errors():
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     rc = lib.gdn_window_batch(ptr(ds.series), None, 1, 9, 8, ptr(ends), 3, ptr(xb), ptr(yb), None, ptr(err),
                               torch.cuda.current_stream().cuda_stream)
-    assert rc == 0 and err.item() in (2, 3) and yb.flatten().tolist() == [8.0, -1.0, -1.0]
+    # ... and hands zeros, never uninitialised memory, to whoever ignores the flag
+    assert rc == 0 and err.item() in (2, 3) and yb.flatten().tolist() == [8.0, 0.0, 0.0]
+    assert xb[1:].abs().max().item() == 0.0
     assert lib.gdn_window_batch(ptr(ds.series), None, 1, 9, 9, ptr(ends), 3, ptr(xb), ptr(yb), None, ptr(err), None) < 0
 
 
