@@ -157,29 +157,29 @@ WsLayout ws_layout(const Shape& s, bool fused) {
     const size_t nb = (size_t)s.N * s.Bs * sizeof(float);
     L.gsiT = take(&off, nb);
     L.gsjT = take(&off, nb);
+    L.tail_ctr = take(&off, 256);
     size_t rec = (size_t)s.D * s.W + s.D;
     if ((size_t)3 * s.D + 32 > rec) rec = (size_t)3 * s.D + 32;
     if ((size_t)s.W * s.W + s.W > rec) rec = (size_t)s.W * s.W + s.W;
     L.part_bytes = (size_t)4 * num_sms() * rec * sizeof(double);
     L.part = take(&off, L.part_bytes);
     L.gV = take(&off, (fused && s.S > 1) ? (size_t)s.S * s.N * s.D * sizeof(float) : 0);
-    // small: c2[2D] c1[2D] gev[2N] part_u[2*sms*64] part_e[2*sms*2D]   (floats)
-    L.small = take(&off, ((size_t)4 * s.D + 2 * s.N + (size_t)2 * num_sms() * (64 + 2 * s.D)) * sizeof(float));
+    // small: c2[2D] c1[2D] part_u[sms*64] part_e[sms*2D]   (floats)
+    L.small = take(&off, ((size_t)4 * s.D + (size_t)num_sms() * (64 + 2 * s.D)) * sizeof(float));
     L.sums = take(&off, (rec + 64) * sizeof(double));
     L.total = off;
     return L;
 }
 
 struct Small {
-    float *c2, *c1, *gev, *part_u, *part_e;
+    float *c2, *c1, *part_u, *part_e;
 };
 static Small small_ptrs(const Shape& s, char* ws, const WsLayout& L) {
     Small m;
     float* p = (float*)(ws + L.small);
     m.c2 = p; p += 2 * s.D;
     m.c1 = p; p += 2 * s.D;
-    m.gev = p; p += 2 * s.N;
-    m.part_u = p; p += (size_t)2 * num_sms() * 64;
+    m.part_u = p; p += (size_t)num_sms() * 64;
     m.part_e = p;
     return m;
 }
@@ -313,7 +313,9 @@ int gdn_graphlayer_fwd(const gdn_dims* d, const float* x, const float* V, const 
     (void)ws; (void)ws_bytes;
     prof_enter(st, "@graphlayer_fwd");
     if (int rc = launch_prep(s, x, V, p, ctx, L, st)) return rc;
-    if (int rc = launch_attn_fwd(s, nbr, ctx, L, alpha, st)) return rc;
+    int fused_out = 0;
+    if (int rc = launch_attn_fwd(s, nbr, ctx, L, alpha, p, out, &fused_out, st)) return rc;
+    if (fused_out) return 0;
     return launch_lin_fwd(s, (const float*)(ctx + L.A), p, out, st);
 }
 
@@ -334,15 +336,14 @@ int gdn_graphlayer_bwd(const gdn_dims* d, const float* g_out, const float* V, co
     const Small sm = small_ptrs(s, ws, WL);
     float* gA = (float*)(ws + WL.gA);
     double* part = (double*)(ws + WL.part);
-    int nrec = 0, nrec_u = 0, nrec_e = 0;
+    int nrec = 0;
     prof_enter(st, "@graphlayer_bwd");
     if (int rc = launch_lin_bwd(s, g_out, (const float*)(ctx + L.A), p, gA, part, &nrec, st)) return rc;
-    if (int rc = launch_attn_bwd(s, nbr, ctx, L, gA, (float*)(ws + WL.gsiT), (float*)(ws + WL.gsjT), sm.gev,
-                                 sm.part_u, &nrec_u, st)) return rc;
-    double* sums = (double*)(ws + WL.sums);
-    if (int rc = launch_fin_layer(s, part, nrec, sm.part_u, nrec_u, sums, p, g, st)) return rc;
-    if (int rc = launch_embed_grads(s, V, sm.gev, p, 0, g->embedding, sm.part_e, &nrec_e, st)) return rc;
-    return launch_fin_embed(s, sm.part_e, nrec_e, sums, g, st);
+    float* gsiT = (float*)(ws + WL.gsiT);
+    float* gsjT = (float*)(ws + WL.gsjT);
+    if (int rc = launch_attn_bwd(s, nbr, ctx, L, gA, gsiT, gsjT, WL.tail_ctr + 256 - WL.gsjT, st)) return rc;
+    return launch_attn_tail(s, ctx, L, V, p, gsiT, gsjT, 0, part, nrec, sm.part_u, sm.part_e, (double*)(ws + WL.sums),
+                            (unsigned int*)(ws + WL.tail_ctr), g, st);
 }
 
 // ------------------------------------------------------------------------------- fused GDN
@@ -376,7 +377,7 @@ int gdn_fused_fwd(const gdn_dims* d, const float* x, const float* V, const int32
     double* part = (double*)(ws + WL.part);
     prof_enter(st, "@fused_fwd");
     if (int rc = launch_prep(s, x, V, p, ctx, L, st)) return rc;
-    if (int rc = launch_attn_fwd(s, nbr, ctx, L, nullptr, st)) return rc;
+    if (int rc = launch_attn_fwd(s, nbr, ctx, L, nullptr, nullptr, nullptr, nullptr, st)) return rc;
     const HeadArgs ha = head_args(s, ctx, L, V, p, h, dp, training);
     if (training) {
         int nrec = 0;
@@ -415,17 +416,17 @@ int gdn_fused_bwd(const gdn_dims* d, const float* g_pred, const float* V, const 
     ba.c1 = sm.c1;
     ba.gV = s.S > 1 ? (float*)(ws + WL.gV) : g->embedding;
     ba.gA = (float*)(ws + WL.gA);
-    int nrec = 0, nrec_u = 0, nrec_e = 0;
+    int nrec = 0;
     prof_enter(st, "@fused_bwd");
     double* sums = (double*)(ws + WL.sums);
     if (int rc = launch_bwd1(s, ha, ba, part, sums, gh, sm.c2, st)) return rc;
     if (int rc = launch_bwd2(s, ha, ba, part, sums, gh, sm.c1, g->embedding, st)) return rc;
     if (int rc = launch_bwd3(s, ha, ba, part, &nrec, st)) return rc;
-    if (int rc = launch_attn_bwd(s, nbr, ctx, L, ba.gA, (float*)(ws + WL.gsiT), (float*)(ws + WL.gsjT), sm.gev,
-                                 sm.part_u, &nrec_u, st)) return rc;
-    if (int rc = launch_fin_layer(s, part, nrec, sm.part_u, nrec_u, sums, p, g, st)) return rc;
-    if (int rc = launch_embed_grads(s, V, sm.gev, p, 1, g->embedding, sm.part_e, &nrec_e, st)) return rc;
-    return launch_fin_embed(s, sm.part_e, nrec_e, sums, g, st);
+    float* gsiT = (float*)(ws + WL.gsiT);
+    float* gsjT = (float*)(ws + WL.gsjT);
+    if (int rc = launch_attn_bwd(s, nbr, ctx, L, ba.gA, gsiT, gsjT, WL.tail_ctr + 256 - WL.gsjT, st)) return rc;
+    return launch_attn_tail(s, ctx, L, V, p, gsiT, gsjT, 1, part, nrec, sm.part_u, sm.part_e, sums,
+                            (unsigned int*)(ws + WL.tail_ctr), g, st);
 }
 
 int gdn_ctx_alpha(const gdn_dims* d, const int32_t* nbr, const void* ctx_, float* alpha, void* stream) {

@@ -83,6 +83,7 @@ struct WsLayout {
     size_t gA;       // [n][W]
     size_t gsiT;     // [N][Bs]
     size_t gsjT;     // [N][Bs]
+    size_t tail_ctr; // one unsigned int right behind gsjT: k_attn_tail's ticket counter, zeroed by the same memset
     size_t part;     // per-CTA partial sums (doubles), size part_bytes
     size_t part_bytes;
     size_t gV;       // [S][N][D] partial embedding gradients (S > 1)

@@ -1536,55 +1536,6 @@ __global__ void k_reduce_gV(const float* __restrict__ gVp, int S, long long ND, 
     }
 }
 
-// layer parameter gradients:
-//   g_Wl[d,w] = main[d,w] + a_i[d] g_ui[w] + a_j[d] g_uj[w];  g_bias = main
-//   g_a_i[d] = sum_w Wl[d,w] g_ui[w];  g_a_j likewise
-__global__ void k_fin_layer(const double* __restrict__ part, int nrec,
-                            const double* __restrict__ part_u, int nrec_u, int W, int D,
-                            const float* __restrict__ Wl, const float* __restrict__ a_i, const float* __restrict__ a_j,
-                            float* __restrict__ g_Wl, float* __restrict__ g_bias,
-                            float* __restrict__ g_ai, float* __restrict__ g_aj) {
-    __shared__ double gu[64];
-    if (threadIdx.x < 64) {
-        double s = 0.0;
-        for (int q = 0; q < nrec_u; ++q) s += (double)part_u[(size_t)q * 64 + threadIdx.x];
-        gu[threadIdx.x] = s;
-    }
-    __syncthreads();
-    const size_t rec = (size_t)D * W + D;
-    for (int e = threadIdx.x; e < D * W + D; e += blockDim.x) {
-        double s = 0.0;
-        for (int q = 0; q < nrec; ++q) s += part[(size_t)q * rec + e];
-        if (e < D * W) {
-            const int d = e / W, w = e % W;
-            s += (double)a_i[d] * gu[w] + (double)a_j[d] * gu[32 + w];
-            g_Wl[e] = (float)s;
-        } else if (g_bias != nullptr) {
-            g_bias[e - D * W] = (float)s;
-        }
-    }
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        double si = 0.0, sj = 0.0;
-        for (int w = 0; w < W; ++w) {
-            const double wl = (double)Wl[(size_t)d * W + w];
-            si += wl * gu[w];
-            sj += wl * gu[32 + w];
-        }
-        g_ai[d] = (float)si;
-        g_aj[d] = (float)sj;
-    }
-}
-
-__global__ void k_fin_embed(const double* __restrict__ part, int nrec, int D,
-                            float* __restrict__ g_aei, float* __restrict__ g_aej) {
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        double si = 0.0, sj = 0.0;
-        for (int q = 0; q < nrec; ++q) { si += (double)part[(size_t)q * 2 * D + d]; sj += (double)part[(size_t)q * 2 * D + D + d]; }
-        g_aei[d] = (float)si;
-        g_aej[d] = (float)sj;
-    }
-}
-
 // ---------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------
@@ -1843,24 +1794,6 @@ int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd3");
     *nrec = grid;
-    return 0;
-}
-
-int launch_fin_layer(const Shape& s, const double* part, int nrec, const float* part_u, int nrec_u, double* sums,
-                     const gdn_layer_params* p, gdn_layer_grads* g, cudaStream_t st) {
-    const int rec = s.D * s.W + s.D;
-    if (int rc = reduce_part<double>(part, nrec, rec, sums, st)) return rc;
-    if (int rc = reduce_part<float>(part_u, nrec_u, 64, sums + rec, st)) return rc;
-    k_fin_layer<<<1, 256, 0, st>>>(sums, 1, sums + rec, 1, s.W, s.D, p->lin_weight, p->att_i, p->att_j,
-                                   g->lin_weight, g->bias, g->att_i, g->att_j);
-    GDN_CHECK_LAUNCH("k_fin_layer");
-    return 0;
-}
-
-int launch_fin_embed(const Shape& s, const float* part, int nrec, double* sums, gdn_layer_grads* g, cudaStream_t st) {
-    if (int rc = reduce_part<float>(part, nrec, 2 * s.D, sums, st)) return rc;
-    k_fin_embed<<<1, 256, 0, st>>>(sums, 1, s.D, g->att_em_i, g->att_em_j);
-    GDN_CHECK_LAUNCH("k_fin_embed");
     return 0;
 }
 

@@ -32,14 +32,16 @@ struct BwdArgs {
 // attention.cu
 int launch_prep(const Shape& s, const float* x, const float* V, const gdn_layer_params* p,
                 char* ctx, const CtxLayout& L, cudaStream_t st);
-int launch_attn_fwd(const Shape& s, const int32_t* nbr, char* ctx, const CtxLayout& L, float* alpha, cudaStream_t st);
+int launch_attn_fwd(const Shape& s, const int32_t* nbr, char* ctx, const CtxLayout& L, float* alpha,
+                    const gdn_layer_params* p, float* out, int* fused_out, cudaStream_t st);
 int launch_attn_alpha(const Shape& s, const int32_t* nbr, const char* ctx, const CtxLayout& L, float* alpha,
                       cudaStream_t st);
 int launch_attn_bwd(const Shape& s, const int32_t* nbr, const char* ctx, const CtxLayout& L,
-                    const float* gA, float* gsiT, float* gsjT, float* gev, float* part_u, int* n_part_u,
-                    cudaStream_t st);
-int launch_embed_grads(const Shape& s, const float* V, const float* gev, const gdn_layer_params* p,
-                       int accumulate, float* gV, float* part, int* n_part, cudaStream_t st);
+                    const float* gA, float* gsiT, float* gsjT, size_t zero_bytes, cudaStream_t st);
+int launch_attn_tail(const Shape& s, const char* ctx, const CtxLayout& L, const float* V, const gdn_layer_params* p,
+                     const float* gsiT, const float* gsjT, int accumulate, const double* part, int nrec,
+                     float* part_u, float* part_e, double* sums, unsigned int* counter, gdn_layer_grads* g,
+                     cudaStream_t st);
 
 // dwide.cu
 int launch_lin_fwd(const Shape& s, const float* A, const gdn_layer_params* p, float* out, cudaStream_t st);
@@ -58,9 +60,6 @@ int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
 int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
                 float* c1, float* gV_final, cudaStream_t st);
 int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st);
-int launch_fin_layer(const Shape& s, const double* part, int nrec, const float* part_u, int nrec_u, double* sums,
-                     const gdn_layer_params* p, gdn_layer_grads* g, cudaStream_t st);
-int launch_fin_embed(const Shape& s, const float* part, int nrec, double* sums, gdn_layer_grads* g, cudaStream_t st);
 
 // graph_build.cu
 size_t graph_build_ws_bytes(int N, int D, int K);
