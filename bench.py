@@ -28,8 +28,8 @@ WORKLOADS = {
     "C1": dict(N=27, W=5, D=64, K=5, B=32, cpu_B=32, desc="MSL demo (run.sh)"),
     "C2": dict(N=51, W=5, D=64, K=15, B=128, cpu_B=128, desc="SWaT-shaped"),
     "C3": dict(N=127, W=5, D=128, K=30, B=256, cpu_B=64, desc="WADI-shaped"),
-    "C4": dict(N=4096, W=16, D=128, K=32, B=64, cpu_B=2, desc="scale-up synthetic"),
-    "C5": dict(N=16384, W=16, D=128, K=64, B=64, cpu_B=1, desc="8xB200 data-parallel config, per-GPU shard"),
+    "C4": dict(N=4096, W=16, D=128, K=32, B=64, cpu_B=8, desc="scale-up synthetic"),
+    "C5": dict(N=16384, W=16, D=128, K=64, B=64, cpu_B=2, desc="8xB200 data-parallel config, per-GPU shard"),
 }
 METRIC = "train windows/sec"
 UNIT = "windows/s"
@@ -65,16 +65,72 @@ def config_dict(name, wl, n_gpus, extra=None):
 
 
 # --------------------------------------------------------------------------------------- CPU arm
+def reference_root():
+    """Where the reference's own files can be imported from: an install under baseline/_ref (if the driver put one
+    there) or the read-only tree of the build container.  Neither exists on a GPU box -> None -> the oracle port."""
+    for root in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(root, "models", "GDN.py")) and os.path.isfile(os.path.join(root, "models", "graph_layer.py")):
+            return root
+    return None
+
+
+class _ReferenceTrainer:
+    """The reference's OWN models/GDN.py + models/graph_layer.py (imported unmodified through the PyG-1.5.0 stand-in,
+    oracle/pyg_shim.py) driven exactly like train.py:31,68-73 on the host cores."""
+    kind = "reference"
+
+    def __init__(self, root, N, W, D, K):
+        import torch
+        from oracle import pyg_shim
+        gdn_mod, _, _ = pyg_shim.import_reference(root)
+        torch.manual_seed(5)
+        # edge_index_sets: only len() and .shape[1] are ever used (SURVEY 3.1); a 1-edge stand-in keeps the dead
+        # [2, B*N*(N-1)] cache of models/GDN.py:135-141 out of host memory at N = 16384
+        self.model = gdn_mod.GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K)
+        self.model.train()
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3)
+        self.V = self.model.embedding.weight
+
+    def train_step(self, x, y):
+        import torch.nn.functional as F
+        self.opt.zero_grad()
+        out = self.model(x, None).float()
+        loss = F.mse_loss(out, y, reduction="mean")
+        loss.backward()
+        self.opt.step()
+        return float(loss.item())
+
+
+class _PortTrainer:
+    kind = "port"
+
+    def __init__(self, N, W, D, K):
+        from oracle import gdn_oracle as go
+        self.tr = go.OracleTrainer(go.init_state(N, D, W, seed=5), K)
+        self.V = self.tr.sd["embedding.weight"]
+
+    def train_step(self, x, y):
+        return self.tr.train_step(x, y)
+
+
 def cpu_train_baseline(name, wl, budget_s, steps=None, warmup=1):
-    """The reference's CPU path (oracle port: same op sequence as models/GDN.py +
-    graph_layer.py, validated against the reference's files) on all host cores."""
+    """The reference's CPU path (`run.sh cpu`) on all host cores: the reference's own files when they are importable
+    here (kind "reference"), else the oracle port -- same op sequence as models/GDN.py + graph_layer.py, pinned to the
+    reference's files by tests/golden (kind "port").  A bounded sample: `cpu_B` windows per step."""
     import torch
     from oracle import gdn_oracle as go
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     N, W, D, K, Bc = wl["N"], wl["W"], wl["D"], wl["K"], wl["cpu_B"]
-    sd = go.init_state(N, D, W, seed=5)
-    tr = go.OracleTrainer(sd, K)
+    root = reference_root()
+    tr = None
+    if root is not None:
+        try:
+            tr = _ReferenceTrainer(root, N, W, D, K)
+        except Exception as e:                                  # a broken install must not take the arm down
+            sys.stderr.write(f"reference import from {root} failed ({type(e).__name__}: {e}); using the oracle port\n")
+    if tr is None:
+        tr = _PortTrainer(N, W, D, K)
     g = torch.Generator().manual_seed(5)
     x, y = torch.rand(Bc, N, W, generator=g), torch.rand(Bc, N, generator=g)
     t0 = time.perf_counter()
@@ -87,11 +143,26 @@ def cpu_train_baseline(name, wl, budget_s, steps=None, warmup=1):
     for _ in range(steps):
         tr.train_step(x, y)
     dt = time.perf_counter() - t0
+    # the learned graph (models/GDN.py:143-159) is built once per STEP whatever the batch: its share of a small-batch
+    # CPU step must be known to compare per-window numbers across different batch sizes
+    with torch.no_grad():
+        t1 = time.perf_counter()
+        reps = 2 if N >= 4096 else 10
+        for _ in range(reps):
+            go.learned_graph(tr.V.detach(), K)
+        graph_ms = (time.perf_counter() - t1) / reps * 1e3
+    step_ms = 1e3 * dt / steps
+    per_window_ms = max(step_ms - graph_ms, 0.0) / Bc
     return {
-        "value": Bc * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        "value": Bc * steps / dt, "unit": UNIT, "cores": cores, "kind": tr.kind,
         "sample": f"{steps} train steps of {Bc} window(s) of {name} ({N} sensors) after {max(warmup, 1)} warm-up, "
-                  f"torch CPU fp32, {cores} threads",
-        "ms_per_step": 1e3 * dt / steps, "steps": steps,
+                  f"torch CPU fp32, {cores} threads"
+                  + (f", reference files imported from {root}" if tr.kind == "reference" else ", oracle port (no reference tree on this box)"),
+        "ms_per_step": step_ms, "steps": steps, "windows_per_step": Bc,
+        "graph_build_ms": graph_ms, "graph_build_share": graph_ms / step_ms if step_ms > 0 else None,
+        "value_at_gpu_batch": 1e3 / (per_window_ms + graph_ms / wl["B"]) if per_window_ms > 0 else None,
+        "value_at_gpu_batch_note": f"windows/s if the per-step graph build were amortised over {wl['B']} windows per step "
+                                   "like the GPU arm's (per-window cost of the sample kept): the like-for-like CPU figure",
     }
 
 
@@ -113,8 +184,9 @@ def run_reference_arm(args):
         "steps": steps, "warmup": max(warm, 1), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(name, wl, args.gpus, {"cpu_windows_per_step": wl["cpu_B"]}),
-        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
-                         "sample": res["sample"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "windows_per_step",
+                                             "graph_build_ms", "graph_build_share", "value_at_gpu_batch",
+                                             "value_at_gpu_batch_note")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -257,38 +329,72 @@ def run_ours(args):
     value = world * B * args.steps / (total_ms / 1e3)
 
     # ---- end to end: host buffers -> H2D -> step -> loss back on the host, every step.
-    # The feed is the product's: gdn_b200.data.Prefetcher (pinned staging, copy stream, one batch in
-    # flight) around a plain iterable of CPU batches, i.e. what wraps the reference's DataLoader.
-    from gdn_b200.data import Prefetcher
-    hx = [x.cpu().pin_memory() for x in xs]              # as DataLoader(pin_memory=True) hands them over
-    hy = [y.cpu().pin_memory() for y in ys]
+    # Host batches are what the reference's loader hands to train.py:63-66: PAGEABLE FLOAT64 tensors
+    # (datasets/TimeDataset.py:64-73 yields doubles, main.py:84-85 DataLoader without pin_memory); the cast to fp32,
+    # the staging into pinned memory and the H2D copy all sit inside the timed region.  The feed is the product's
+    # gdn_b200.data.Prefetcher (worker thread + copy stream, one batch in flight), the loss comes back every step
+    # through gdn_b200.data.LossReader (4 bytes D2H per step, read one step late instead of a sync per step).
+    from gdn_b200.data import LossReader, Prefetcher
+    hx64 = [x.cpu().double() for x in xs]                # pageable, float64
+    hy64 = [y.cpu().double() for y in ys]
     losses = []
 
-    def host_batches(count):
+    def host_batches(hxs, hys, count):
         for i in range(count):
-            yield hx[i % nbuf], hy[i % nbuf]
+            yield hxs[i % nbuf], hys[i % nbuf]
 
-    def e2e_run(count):
-        for bx, by in Prefetcher(host_batches(count), dev, skip=(), reuse_buffers=True):
-            losses.append(trainer.step(bx, by).item())       # D2H + sync every step, as train.py:76
+    def e2e_run(hxs, hys, count, threaded, deferred):
+        reader = LossReader(dev) if deferred else None
+        for bx, by in Prefetcher(host_batches(hxs, hys, count), dev, skip=(), reuse_buffers=True, threaded=threaded):
+            loss = trainer.step(bx, by)
+            if deferred:
+                v = reader.push(loss)
+                if v is not None:
+                    losses.append(v)
+            else:
+                losses.append(loss.item())                   # D2H + sync every step, as train.py:76
+        if deferred:
+            losses.extend(reader.flush())
 
-    e2e_run(3)
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    e2e_run(args.steps)
-    t1.record()
-    barrier()
-    e2e_ms = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    def e2e_timed(hxs, hys, threaded, deferred):
+        e2e_run(hxs, hys, 3, threaded, deferred)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        t0.record()
+        e2e_run(hxs, hys, args.steps, threaded, deferred)
+        t1.record()
+        barrier()
+        ms = max(t0.elapsed_time(t1), (time.perf_counter() - w0) * 1e3 if deferred else 0.0)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    e2e_ms = e2e_timed(hx64, hy64, threaded=True, deferred=True)
+    n_losses = len(losses)
     e2e = {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": UNIT,
            "h2d_bytes_per_step": int(xs[0].numel() * 4 + ys[0].numel() * 4), "d2h_bytes_per_step": 4,
-           "ms_per_step": e2e_ms / args.steps, "last_loss": losses[-1]}
+           "ms_per_step": e2e_ms / args.steps, "last_loss": losses[-1], "losses_read": n_losses,
+           "host_batches": "pageable float64 [B,N,W] + [B,N] as the reference's DataLoader yields them "
+                           "(datasets/TimeDataset.py:64-73); fp32 cast + pinned staging on a worker thread inside the timed region",
+           "host_bytes_staged_per_step": int(xs[0].numel() * 8 + ys[0].numel() * 8)}
+    # the round-1 variant for comparison: batches already pinned fp32, blocking loss.item() every step
+    if not args.no_extras:
+        hx = [x.cpu().pin_memory() for x in xs]
+        hy = [y.cpu().pin_memory() for y in ys]
+        ms2 = e2e_timed(hx, hy, threaded=False, deferred=False)
+        e2e["pinned_fp32_blocking_item"] = {"value": world * B * args.steps / (ms2 / 1e3), "ms_per_step": ms2 / args.steps,
+                                            "what": "host batches pre-pinned fp32 (DataLoader(pin_memory=True) + a float32 dataset), "
+                                                    "loss.item() sync every step"}
+        ms3 = e2e_timed(hx64, hy64, threaded=False, deferred=False)
+        e2e["pageable_f64_blocking_item"] = {"value": world * B * args.steps / (ms3 / 1e3), "ms_per_step": ms3 / args.steps,
+                                             "what": "pageable float64 batches staged on the calling thread, loss.item() sync every "
+                                                     "step: train.py:63-77 unchanged around the drop-in model"}
+        del hx, hy
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- the same step captured into a CUDA graph (single GPU): what the launch-bound configs gain
     graph_info = None

@@ -462,6 +462,18 @@ int gdn_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_
                             (cudaStream_t)stream);
 }
 
+int gdn_nvls_adam(const float* params_local, float* params_mc, const float* grads_mc, float* exp_avg, float* exp_avg_sq,
+                  long long lo, long long count, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  long long step, float grad_scale, void* stream) {
+    GDN_CHECK_ARG(params_local && params_mc && grads_mc && exp_avg && exp_avg_sq, "nvls_adam: NULL argument");
+    GDN_CHECK_ARG(lo >= 0 && count >= 4 && (lo % 4) == 0 && (count % 4) == 0, "nvls_adam: slice [%lld, +%lld) must be 16-byte aligned", lo, count);
+    GDN_CHECK_ARG(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && lr >= 0.f,
+                  "nvls_adam: bad hyper-parameters (step=%lld)", step);
+    prof_enter((cudaStream_t)stream, "@nvls_adam");
+    return launch_nvls_adam(params_local, params_mc, grads_mc, exp_avg, exp_avg_sq, lo, count, lr, beta1, beta2, eps,
+                            weight_decay, step, grad_scale, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------- metrics
 int gdn_f1_sweep(const double* sorted_scores, const float* labels_sorted, int T, const int* k_pred, const int* k_thr,
                  int S, double* fmeas, double* thresholds, void* stream) {

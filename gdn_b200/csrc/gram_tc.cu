@@ -620,19 +620,22 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int row0, 
     if (idx_out != nullptr)
         for (int k = lane; k < K; k += 32) idx_out[(size_t)i * K + k] = (int64_t)s_out[wid][k];
     if (nbr_out != nullptr) {
-        // neighbour list: the top-k without the row itself, then the row itself, then -1 padding
+        // neighbour list: the top-k without the row itself, then the row itself, then negative padding; the last slot
+        // also records where the row itself sat in the top-k (-2 - position): idx can be rebuilt from this table alone
         int32_t* nb = nbr_out + (size_t)i * (K + 1);
         const unsigned lt = (1u << lane) - 1u;
-        int o = 0;
+        int o = 0, pos = -1;
         for (int k0 = 0; k0 < K; k0 += 32) {
             const int k = k0 + lane;
             const int j = k < K ? s_out[wid][k] : i;
             const unsigned m = __ballot_sync(0xffffffffu, j != i);
+            const unsigned ms = __ballot_sync(0xffffffffu, k < K && j == i);
+            if (pos < 0 && ms != 0u) pos = k0 + __ffs(ms) - 1;
             if (j != i) nb[o + __popc(m & lt)] = j;
             o += __popc(m);
         }
         if (lane == 0) nb[o] = i;
-        for (int k = o + 1 + lane; k < K + 1; k += 32) nb[k] = -1;
+        for (int k = o + 1 + lane; k < K + 1; k += 32) nb[k] = (k == K && pos >= 0) ? -2 - pos : -1;
     }
 }
 

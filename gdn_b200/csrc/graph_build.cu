@@ -174,13 +174,16 @@ k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, i
         if (kth_out != nullptr && lane == 0) kth_out[gi] = cnt >= K ? lvals[(size_t)r * K + K - 1] : -INFINITY;
         if (nbr_out != nullptr && lane == 0) {
             int32_t* nb = nbr_out + (size_t)gi * (K + 1);
-            int o = 0;
+            int o = 0, pos = -1;
             for (int k = 0; k < K; ++k) {
                 const int j = k < cnt ? idxs[k] : gi;
                 if (j != gi) nb[o++] = j;
+                else if (pos < 0) pos = k;
             }
             nb[o++] = gi;
-            for (; o < K + 1; ++o) nb[o] = -1;
+            // padding: any negative value ends the list; the last slot also records where the row itself sat in
+            // the top-k (-2 - position), so that idx can be rebuilt from this table alone (data-parallel exchange)
+            for (; o < K + 1; ++o) nb[o] = (o == K && pos >= 0) ? -2 - pos : -1;
         }
     }
 }

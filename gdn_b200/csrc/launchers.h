@@ -71,6 +71,10 @@ int launch_graph_build(const float* V, int N, int D, int K, int row0, int row1, 
 int launch_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                      float eps, float weight_decay, long long step, float grad_scale, cudaStream_t st);
 
+int launch_nvls_adam(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, long long lo, long long cnt,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale,
+                     cudaStream_t st);
+
 // metrics.cu
 int launch_f1_sweep(const double* sorted_scores, const float* labels_sorted, int T, const int* k_pred, const int* k_thr,
                     int S, double* fmeas, double* thresholds, cudaStream_t st);

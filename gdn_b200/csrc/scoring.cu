@@ -7,17 +7,24 @@
 //   err[t] = (delta[t] - med) / (|iqr| + 1e-2)
 //   s[t] = mean(err[t-3 .. t]) for t >= 3, else 0;   top1[t] = max_i s_i[t]
 //
-// Pipeline: (1) |pred-gt| transposed to sensor-major float64; (2) one CTA per sensor finds
-// the six order statistics the median / quartiles need with an MSB-first radix select over
-// the float64 bit patterns (non-negative doubles order like their bits) -- no sort, eight
-// passes over the series; (3) one kernel normalises, smooths and takes the max over sensors.
+// Two kernels:
+//  (1) k_delta_transpose: |pred - gt| transposed to sensor-major float64 (32x32 tiles through shared memory, both
+//      sides coalesced); also seeds top1 with -inf.
+//  (2) k_score_sensor: one CTA per sensor.  The sensor's series is pulled into shared memory once (up to
+//      SC_RESIDENT ticks; longer series are streamed from L2 by every pass), the six order statistics the median
+//      and the quartiles need come from an MSB-first radix select over the float64 bit patterns (non-negative
+//      doubles order like their bits) that starts at the highest bit in which the series' min and max differ, the
+//      normalised errors overwrite the series in place, and the trailing mean is written out.  The max over
+//      sensors is an ordered-integer atomic max per tick, issued only when the value beats what is already there.
+// HBM traffic: 8TN read + 8TN written by (1), 8TN read + 8TN written by (2): 4x the output size.
+#include <stdlib.h>
 #include "common.cuh"
 #include "launchers.h"
 
 namespace gdn {
 
 __global__ void k_delta_transpose(const float* __restrict__ pred, const float* __restrict__ gt, int T, int N,
-                                  double* __restrict__ dT) {
+                                  double* __restrict__ dT, double* __restrict__ top1) {
     __shared__ double tile[32][33];
     const int t0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -26,6 +33,7 @@ __global__ void k_delta_transpose(const float* __restrict__ pred, const float* _
         if (t < T && i < N) v = fabs((double)pred[(size_t)t * N + i] - (double)gt[(size_t)t * N + i]);
         tile[r][threadIdx.x] = v;
     }
+    if (top1 != nullptr && blockIdx.y == 0 && threadIdx.y == 0 && t0 + threadIdx.x < T) top1[t0 + threadIdx.x] = -INFINITY;
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int i = i0 + r, t = t0 + threadIdx.x;
@@ -34,6 +42,7 @@ __global__ void k_delta_transpose(const float* __restrict__ pred, const float* _
 }
 
 #define SC_NQ 6
+#define SC_RESIDENT 24576            // ticks of one sensor kept in shared memory (192 KB)
 
 // numpy 'linear' interpolation between order statistics a <= b at fraction t
 __device__ __forceinline__ double np_lerp(double a, double b, double t) {
@@ -41,111 +50,419 @@ __device__ __forceinline__ double np_lerp(double a, double b, double t) {
     return t < 0.5 ? __dadd_rn(a, __dmul_rn(d, t)) : __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t)));
 }
 
-__global__ void __launch_bounds__(256)
-k_select_stats(const double* __restrict__ dT, int T, double* __restrict__ stats) {
-    __shared__ unsigned hist[SC_NQ][256];
-    __shared__ unsigned long long prefix[SC_NQ];
-    __shared__ long long rank[SC_NQ];       // rank still to find inside the current prefix
-    __shared__ double frac[2];
-    const int i = blockIdx.x;
-    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(dT + (size_t)i * T);
-    if (threadIdx.x == 0) {
+// max over sensors: doubles ordered through their bit patterns (non-negative: as signed integers, ascending;
+// negative: as unsigned integers, descending) -- the result does not depend on the order of arrival
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+    if (v >= 0.0) atomicMax(reinterpret_cast<long long*>(addr), __double_as_longlong(v));
+    else atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+extern __shared__ __align__(16) unsigned char score_smem[];
+
+// ---------------------------------------------------------------------------------------------------------------
+// order statistics of one sensor by MSB-first radix select, shared by both kernels below.
+// The CTA's threads hold / stream the series through `KeyAt` (keys = float64 bit patterns, all non-negative).
+// Passes of 8 bits run from the highest bit in which min and max differ; ranks whose prefixes coincide share a
+// histogram; as soon as every rank's bucket holds <= 32 elements a last sweep collects the bucket members and a
+// warp ranks them by counting -- typically 2-3 sweeps + 1 instead of 8.
+// ---------------------------------------------------------------------------------------------------------------
+struct SelectShared {
+    unsigned hist[SC_NQ][256];
+    unsigned long long cand[SC_NQ][32];
+    unsigned long long prefix[SC_NQ];      // bits above the current digit of the element of rank q
+    unsigned long long value[SC_NQ];       // the selected keys
+    long long rank[SC_NQ];                 // rank still to find inside that prefix
+    unsigned count[SC_NQ];                 // elements sharing that prefix
+    unsigned ncand[SC_NQ];
+    int group[SC_NQ];                      // first rank with the same prefix (shares its histogram / candidates)
+    unsigned char next[SC_NQ][256];        // (group, digit) of the last sweep -> group after it, 7 = no rank left there
+    unsigned long long wmin[8], wmax[8];
+    double frac[2];
+};
+
+__device__ __forceinline__ void select_init(SelectShared& S, int T, unsigned long long kmin, unsigned long long kmax, int* bits_out) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmin = a < kmin ? a : kmin;
+        kmax = b > kmax ? b : kmax;
+    }
+    if (lane == 0) { S.wmin[wid] = kmin; S.wmax[wid] = kmax; }
+    __syncthreads();
+    for (int w = 0; w < 8; ++w) {
+        kmin = S.wmin[w] < kmin ? S.wmin[w] : kmin;
+        kmax = S.wmax[w] > kmax ? S.wmax[w] : kmax;
+    }
+    const unsigned long long diff = kmin ^ kmax;
+    const int bits = diff == 0ull ? 0 : 64 - __clzll((long long)diff);   // low bits in which the keys can differ (< 64: sign bits agree)
+    if (tid == 0) {
         const double p25 = 0.25 * (double)(T - 1), p75 = 0.75 * (double)(T - 1);
         const long long l25 = (long long)floor(p25), l75 = (long long)floor(p75);
-        rank[0] = (T - 1) / 2;                               // lower median
-        rank[1] = T / 2;                                     // upper median
-        rank[2] = l25;
-        rank[3] = l25 + 1 < T ? l25 + 1 : T - 1;
-        rank[4] = l75;
-        rank[5] = l75 + 1 < T ? l75 + 1 : T - 1;
-        frac[0] = p25 - (double)l25;
-        frac[1] = p75 - (double)l75;
-        for (int q = 0; q < SC_NQ; ++q) prefix[q] = 0ull;
+        S.rank[0] = (T - 1) / 2;                               // lower median
+        S.rank[1] = T / 2;                                     // upper median
+        S.rank[2] = l25;
+        S.rank[3] = l25 + 1 < T ? l25 + 1 : T - 1;
+        S.rank[4] = l75;
+        S.rank[5] = l75 + 1 < T ? l75 + 1 : T - 1;
+        S.frac[0] = p25 - (double)l25;
+        S.frac[1] = p75 - (double)l75;
+        for (int q = 0; q < SC_NQ; ++q) { S.prefix[q] = kmin >> bits; S.group[q] = 0; S.count[q] = (unsigned)T; S.ncand[q] = 0u; }
     }
     __syncthreads();
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 56 - 8 * pass;
-        for (int e = threadIdx.x; e < SC_NQ * 256; e += blockDim.x) (&hist[0][0])[e] = 0u;
-        __syncthreads();
-        unsigned long long pf[SC_NQ];
+    *bits_out = bits;
+}
+
+// histogram contribution of one key (any thread subset may call it)
+__device__ __forceinline__ void select_count(SelectShared& S, unsigned long long k, int bits, int shift, unsigned mask,
+                                             const unsigned long long (&pf)[SC_NQ], const int (&lead)[SC_NQ]) {
+    const unsigned long long hi = k >> bits;
+    const unsigned dig = (unsigned)(k >> shift) & mask;
 #pragma unroll
-        for (int q = 0; q < SC_NQ; ++q) pf[q] = prefix[q];
-        for (int t = threadIdx.x; t < T; t += blockDim.x) {
-            const unsigned long long k = keys[t];
-            const unsigned long long hi = pass == 0 ? 0ull : (k >> (shift + 8));
-            const unsigned dig = (unsigned)(k >> shift) & 255u;
-#pragma unroll
-            for (int q = 0; q < SC_NQ; ++q)
-                if (hi == pf[q]) atomicAdd(&hist[q][dig], 1u);
+    for (int q = 0; q < SC_NQ; ++q)
+        if (lead[q] && hi == pf[q]) {
+            // lanes of the warp that hit the same bin add once: the first passes see a handful of exponents
+            const unsigned peers = __match_any_sync(__activemask(), dig);
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&S.hist[q][dig], (unsigned)__popc(peers));
         }
-        __syncthreads();
-        if (threadIdx.x < SC_NQ) {
-            const int q = threadIdx.x;
-            long long r = rank[q];
-            int dsel = 255;
-            for (int dgt = 0; dgt < 256; ++dgt) {
-                const long long c = (long long)hist[q][dgt];
-                if (r < c) { dsel = dgt; break; }
-                r -= c;
+}
+
+// after a counting sweep: warp q walks the histogram of its group (8 bins per lane), narrows rank q
+__device__ __forceinline__ void select_narrow(SelectShared& S, int w) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __syncthreads();
+    if (wid < SC_NQ) {
+        const int q = wid;
+        const unsigned* h = S.hist[S.group[q]];
+        unsigned c[8], tot = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { c[u] = h[lane * 8 + u]; tot += c[u]; }
+        unsigned incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const long long r = S.rank[q];
+        const long long before = (long long)(incl - tot);
+        if (r >= before && r < (long long)incl) {
+            long long rr = r - before;
+            int usel = 7;
+            unsigned csel = c[7];
+            bool found = false;
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                if (!found) {
+                    if (rr < (long long)c[u]) { usel = u; csel = c[u]; found = true; }
+                    else rr -= (long long)c[u];
+                }
             }
-            rank[q] = r;
-            prefix[q] = (prefix[q] << 8) | (unsigned long long)dsel;
+            S.rank[q] = rr;
+            S.count[q] = csel;
+            S.prefix[q] = (S.prefix[q] << w) | (unsigned long long)(lane * 8 + usel);
         }
-        __syncthreads();
     }
+    for (int e = tid; e < SC_NQ * 256 / 4; e += blockDim.x) reinterpret_cast<unsigned*>(&S.next[0][0])[e] = 0x07070707u;
+    __syncthreads();
+    if (tid < SC_NQ) {
+        int g = tid;
+        for (int q2 = 0; q2 < tid; ++q2)
+            if (S.prefix[q2] == S.prefix[tid]) { g = q2; break; }
+        // ranks that shared a group and picked the same digit share the new prefix, hence the new group: consistent
+        S.next[S.group[tid]][(unsigned)S.prefix[tid] & ((1u << w) - 1u)] = (unsigned char)g;
+        __syncwarp(0x3fu);
+        S.group[tid] = g;
+    }
+    for (int e = tid; e < SC_NQ * 256; e += blockDim.x) (&S.hist[0][0])[e] = 0u;
+    __syncthreads();
+}
+
+__device__ __forceinline__ void select_collect(SelectShared& S, unsigned long long k, int bits,
+                                               const unsigned long long (&pf)[SC_NQ], const int (&lead)[SC_NQ]) {
+    const unsigned long long hi = k >> bits;
+#pragma unroll
+    for (int q = 0; q < SC_NQ; ++q)
+        if (lead[q] && hi == pf[q]) {
+            const unsigned pos = atomicAdd(&S.ncand[q], 1u);
+            if (pos < 32u) S.cand[q][pos] = k;
+        }
+}
+
+// warp q ranks the <= 32 members of its bucket by counting; ties are interchangeable (equal keys)
+__device__ __forceinline__ void select_finish(SelectShared& S, int bits) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __syncthreads();
+    if (wid < SC_NQ) {
+        const int q = wid, g = S.group[q];
+        if (bits == 0) {
+            if (lane == 0) S.value[q] = S.prefix[q];
+        } else {
+            const int n = (int)S.count[q];
+            const unsigned long long mine = lane < n ? S.cand[g][lane] : ~0ull;
+            int below = 0;
+            for (int j = 0; j < n; ++j) {
+                const unsigned long long o = __shfl_sync(0xffffffffu, mine, j);
+                below += (o < mine || (o == mine && j < lane)) ? 1 : 0;
+            }
+            if (lane < n && (long long)below == S.rank[q]) S.value[q] = mine;
+        }
+    }
+    __syncthreads();
+}
+
+// median and IQR from the six selected keys -> S.frac[0] = median, S.frac[1] = IQR
+__device__ __forceinline__ void select_stats(SelectShared& S, int T, double* __restrict__ stats, int i) {
     if (threadIdx.x == 0) {
         double v[SC_NQ];
-        for (int q = 0; q < SC_NQ; ++q) v[q] = __longlong_as_double((long long)prefix[q]);
+        for (int q = 0; q < SC_NQ; ++q) v[q] = __longlong_as_double((long long)S.value[q]);
         const double med = (T & 1) ? v[0] : (v[0] + v[1]) / 2.0;
-        const double q25 = np_lerp(v[2], v[3], frac[0]);
-        const double q75 = np_lerp(v[4], v[5], frac[1]);
-        stats[2 * i] = med;
-        stats[2 * i + 1] = q75 - q25;
+        const double q25 = np_lerp(v[2], v[3], S.frac[0]);
+        const double q75 = np_lerp(v[4], v[5], S.frac[1]);
+        S.frac[0] = med;
+        S.frac[1] = q75 - q25;
+        if (stats != nullptr) { stats[2 * i] = med; stats[2 * i + 1] = q75 - q25; }
+    }
+    __syncthreads();
+}
+
+#define SC_SELECT_LOOP(FOR_EACH_KEY_BEGIN, FOR_EACH_KEY_END)                                                       \
+    {                                                                                                             \
+        for (int e__ = threadIdx.x; e__ < SC_NQ * 256; e__ += blockDim.x) (&S.hist[0][0])[e__] = 0u;              \
+        __syncthreads();                                                                                          \
+        unsigned long long pf[SC_NQ];                                                                             \
+        int lead[SC_NQ];                                                                                          \
+        for (;;) {                                                                                                \
+            unsigned worst = 0;                                                                                   \
+            _Pragma("unroll") for (int q = 0; q < SC_NQ; ++q) {                                                   \
+                pf[q] = S.prefix[q]; lead[q] = S.group[q] == q; worst = S.count[q] > worst ? S.count[q] : worst;  \
+            }                                                                                                     \
+            if (bits == 0 || worst <= 32u) break;                                                                 \
+            const int w = bits >= 8 ? 8 : bits, shift = bits - w;                                                 \
+            const unsigned mask = (1u << w) - 1u;                                                                 \
+            FOR_EACH_KEY_BEGIN select_count(S, k, bits, shift, mask, pf, lead); FOR_EACH_KEY_END                  \
+            select_narrow(S, w);                                                                                  \
+            bits = shift;                                                                                         \
+        }                                                                                                         \
+        if (bits > 0) { FOR_EACH_KEY_BEGIN select_collect(S, k, bits, pf, lead); FOR_EACH_KEY_END }               \
+        select_finish(S, bits);                                                                                   \
+    }
+
+// ---------------------------------------------------------------------------------------------------------------
+// (2a) series up to 256 * EPT ticks: the sensor's keys live in REGISTERS for every sweep (thread t holds ticks
+//      t, t + 256, ...); shared memory only carries the normalised errors for the 4-tap trailing mean.
+// ---------------------------------------------------------------------------------------------------------------
+// HM = how a counting sweep builds its histograms: 0 match-aggregated shared atomics (8-bit digits), 1 plain shared
+// atomics (8-bit digits), 2 warp ballots (5-bit digits: lane l counts bin l of every live group in registers, no
+// atomics or matches in the sweep)
+template <int EPT, int HM>
+__global__ void __launch_bounds__(256, EPT <= 16 ? 3 : 1)
+k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ stats,
+                   double* __restrict__ scores, double* __restrict__ top1) {
+    __shared__ SelectShared S;
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31;
+    const unsigned lanebit = 1u << lane;
+    constexpr int WD = HM == 2 ? 5 : 8;                         // digit width
+    unsigned inv[5];                                            // ballot b_j ^ inv[j] = lanes whose digit bit j equals lane's
+#pragma unroll
+    for (int j = 0; j < 5; ++j) inv[j] = ((lane >> j) & 1) ? 0u : 0xffffffffu;
+    const double* row = dT + (size_t)i * T;
+    double* srow = reinterpret_cast<double*>(score_smem);      // [256 * EPT]
+    unsigned long long key[EPT];
+    unsigned char tag[EPT];                                    // group of the element (a rank id), 7 = out of the race
+    // min / max of the keys word by word (integer min/max are one instruction; a double compare-select is a dozen):
+    // the low words only matter when every high word is the same
+    unsigned hmin = 0xffffffffu, hmax = 0u, lmin = 0xffffffffu, lmax = 0u;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int t = tid + 256 * e;
+        key[e] = t < T ? (unsigned long long)__double_as_longlong(row[t]) : 0ull;
+        tag[e] = t < T ? 0 : 7;
+        if (t < T) {
+            const unsigned hi = (unsigned)(key[e] >> 32), lo = (unsigned)key[e];
+            hmin = min(hmin, hi); hmax = max(hmax, hi);
+            lmin = min(lmin, lo); lmax = max(lmax, lo);
+        }
+    }
+    // any pair (kmin, kmax) works for select_init as long as every key shares the bits above their highest
+    // differing bit and kmin carries those bits: true for (hmin:lmin, hmax:lmax) -- and exact when the high words agree
+    int bits;
+    select_init(S, T, ((unsigned long long)hmin << 32) | lmin, ((unsigned long long)hmax << 32) | lmax, &bits);
+    for (int e = tid; e < SC_NQ * 256; e += blockDim.x) (&S.hist[0][0])[e] = 0u;
+    __syncthreads();
+    int prev_shift = 0;
+    unsigned prev_mask = 0u;
+    bool swept = false;
+    for (;;) {
+        unsigned worst = 0;
+#pragma unroll
+        for (int q = 0; q < SC_NQ; ++q) worst = S.count[q] > worst ? S.count[q] : worst;
+        const bool last = bits == 0 || worst <= 32u;
+        const int w = bits >= WD ? WD : bits, shift = bits - w;
+        const unsigned mask = (1u << w) - 1u;
+        unsigned cnt[SC_NQ];
+        bool lead[SC_NQ];
+#pragma unroll
+        for (int q = 0; q < SC_NQ; ++q) { cnt[q] = 0u; lead[q] = S.group[q] == q; }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            if (swept && tag[e] != 7) tag[e] = S.next[tag[e]][(unsigned)(key[e] >> prev_shift) & prev_mask];
+            const bool alive = tag[e] != 7;
+            if (__ballot_sync(0xffffffffu, alive) == 0u) continue;
+            if (last) {
+                if (alive && bits > 0) {
+                    const unsigned pos = atomicAdd(&S.ncand[tag[e]], 1u);
+                    if (pos < 32u) S.cand[tag[e]][pos] = key[e];
+                }
+            } else {
+                const unsigned dig = (unsigned)(key[e] >> shift) & mask;
+                if (HM == 0) {
+                    // lanes that hit the same (group, bin) add once: the first sweeps see a handful of exponents
+                    const unsigned peers = __match_any_sync(0xffffffffu, alive ? ((unsigned)tag[e] << 8 | dig) : 0xffffffffu);
+                    if (alive && (peers & (0u - peers)) == lanebit) atomicAdd(&S.hist[tag[e]][dig], (unsigned)__popc(peers));
+                } else if (HM == 1) {
+                    if (alive) atomicAdd(&S.hist[tag[e]][dig], 1u);
+                } else {
+                    unsigned m = __ballot_sync(0xffffffffu, alive);
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) m &= __ballot_sync(0xffffffffu, (dig >> j) & 1u) ^ inv[j];
+#pragma unroll
+                    for (int q = 0; q < SC_NQ; ++q)
+                        if (lead[q]) cnt[q] += (unsigned)__popc(m & __ballot_sync(0xffffffffu, tag[e] == q));
+                }
+            }
+        }
+        if (last) break;
+        if (HM == 2) {
+#pragma unroll
+            for (int q = 0; q < SC_NQ; ++q)
+                if (lead[q] && cnt[q] != 0u) atomicAdd(&S.hist[q][lane], cnt[q]);
+        }
+        select_narrow(S, w);
+        prev_shift = shift;
+        prev_mask = mask;
+        swept = true;
+        bits = shift;
+    }
+    select_finish(S, bits);
+    select_stats(S, T, stats, i);
+    if (scores == nullptr && top1 == nullptr) return;
+    const double med = S.frac[0], den = fabs(S.frac[1]) + 1e-2;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int t = tid + 256 * e;
+        if (t < T) srow[t] = (__longlong_as_double((long long)key[e]) - med) / den;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int t = tid + 256 * e;
+        if (t < T) {
+            double sc = 0.0;
+            if (t >= 3) {
+                double acc = -0.0;
+#pragma unroll
+                for (int q = 3; q >= 0; --q) acc += srow[t - q];
+                sc = acc * 0.25;                                // == acc / 4.0 (power of two)
+            }
+            if (scores != nullptr) scores[(size_t)i * T + t] = sc;
+            if (top1 != nullptr && sc > __ldcg(top1 + t)) atomic_max_double(top1 + t, sc);
+        }
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// (2b) longer series: resident in shared memory up to SC_RESIDENT ticks, else streamed from L2 by every sweep
+// ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_scores(const double* __restrict__ dT, const double* __restrict__ stats, int T, int N,
-         double* __restrict__ scores, double* __restrict__ top1) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    double best = -INFINITY;
-    for (int i = 0; i < N; ++i) {
-        double s = 0.0;
-        if (t >= 3) {
-            const double med = stats[2 * i], den = fabs(stats[2 * i + 1]) + 1e-2;
-            const double* row = dT + (size_t)i * T;
-            double acc = -0.0;
-#pragma unroll
-            for (int q = 3; q >= 0; --q) acc += (row[t - q] - med) / den;
-            s = acc / 4.0;
-        }
-        if (scores != nullptr) scores[(size_t)i * T + t] = s;
-        best = s > best ? s : best;
+k_score_sensor(const double* __restrict__ dT, int T, int resident, double* __restrict__ stats,
+               double* __restrict__ scores, double* __restrict__ top1) {
+    __shared__ SelectShared S;
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const double* row = dT + (size_t)i * T;
+    double* srow = reinterpret_cast<double*>(score_smem);
+    unsigned long long kmin = ~0ull, kmax = 0ull;
+    for (int t = tid; t < T; t += blockDim.x) {
+        const double v = row[t];
+        if (resident) srow[t] = v;
+        const unsigned long long k = (unsigned long long)__double_as_longlong(v);
+        kmin = k < kmin ? k : kmin;
+        kmax = k > kmax ? k : kmax;
     }
-    if (top1 != nullptr) top1[t] = best;
+    int bits;
+    select_init(S, T, kmin, kmax, &bits);
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(resident ? srow : row);
+#define SC_KEYS_BEGIN for (int t = tid; t < T; t += blockDim.x) { const unsigned long long k = keys[t];
+#define SC_KEYS_END }
+    SC_SELECT_LOOP(SC_KEYS_BEGIN, SC_KEYS_END)
+#undef SC_KEYS_BEGIN
+#undef SC_KEYS_END
+    select_stats(S, T, stats, i);
+    if (scores == nullptr && top1 == nullptr) return;
+    const double med = S.frac[0], den = fabs(S.frac[1]) + 1e-2;
+    if (resident) {                                          // one division per tick, in place
+        for (int t = tid; t < T; t += blockDim.x) srow[t] = (srow[t] - med) / den;
+        __syncthreads();
+    }
+    for (int t = tid; t < T; t += blockDim.x) {
+        double sc = 0.0;
+        if (t >= 3) {
+            double acc = -0.0;
+            if (resident) {
+#pragma unroll
+                for (int q = 3; q >= 0; --q) acc += srow[t - q];
+            } else {
+#pragma unroll
+                for (int q = 3; q >= 0; --q) acc += (row[t - q] - med) / den;
+            }
+            sc = acc / 4.0;
+        }
+        if (scores != nullptr) scores[(size_t)i * T + t] = sc;
+        if (top1 != nullptr && sc > __ldcg(top1 + t)) atomic_max_double(top1 + t, sc);
+    }
 }
 
 size_t score_ws_bytes(int T, int N) {
-    return align_up((size_t)T * N * sizeof(double), 256) + align_up((size_t)2 * N * sizeof(double), 256);
+    return align_up((size_t)T * N * sizeof(double), 256);
 }
 
 int launch_score(const float* pred, const float* gt, int T, int N, double* scores, double* top1, double* stats,
                  void* ws, size_t ws_bytes, cudaStream_t st) {
     (void)ws_bytes;
     double* dT = (double*)ws;
-    double* st_int = (double*)((char*)ws + align_up((size_t)T * N * sizeof(double), 256));
-    double* st_out = stats ? stats : st_int;
     dim3 grid(ceil_div(T, 32), ceil_div(N, 32));
     GDN_CHECK_ARG(grid.y <= 65535, "score: too many sensors (%d)", N);
-    k_delta_transpose<<<grid, dim3(32, 8), 0, st>>>(pred, gt, T, N, dT);
+    k_delta_transpose<<<grid, dim3(32, 8), 0, st>>>(pred, gt, T, N, dT, top1);
     GDN_CHECK_LAUNCH("k_delta_transpose");
-    k_select_stats<<<N, 256, 0, st>>>(dT, T, st_out);
-    GDN_CHECK_LAUNCH("k_select_stats");
-    if (scores != nullptr || top1 != nullptr) {
-        k_scores<<<ceil_div(T, 256), 256, 0, st>>>(dT, st_out, T, N, scores, top1);
-        GDN_CHECK_LAUNCH("k_scores");
+    static int hm = -1;                                     // diagnostics: GDN_SCORE_HM = 0 | 1 | 2 (see k_score_sensor_reg)
+    if (hm < 0) { const char* e = getenv("GDN_SCORE_HM"); hm = e ? atoi(e) : 1; }
+#define SC_LAUNCH_REG2(EPTV, HMV)                                                                      \
+    do {                                                                                              \
+        const size_t sm__ = (size_t)256 * (EPTV) * sizeof(double);                                    \
+        cudaError_t e__ = ensure_dyn_smem(k_score_sensor_reg<EPTV, HMV>, sm__);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, "smem attribute k_score_sensor_reg");           \
+        k_score_sensor_reg<EPTV, HMV><<<N, 256, sm__, st>>>(dT, T, stats, scores, top1);              \
+    } while (0)
+#define SC_LAUNCH_REG(EPTV)                                                                            \
+    do {                                                                                              \
+        if (hm == 0) SC_LAUNCH_REG2(EPTV, 0);                                                         \
+        else if (hm == 1) SC_LAUNCH_REG2(EPTV, 1);                                                    \
+        else SC_LAUNCH_REG2(EPTV, 2);                                                                 \
+    } while (0)
+    if (T <= 256 * 4) SC_LAUNCH_REG(4);
+    else if (T <= 256 * 8) SC_LAUNCH_REG(8);
+    else if (T <= 256 * 16) SC_LAUNCH_REG(16);
+    else if (T <= 256 * 32) SC_LAUNCH_REG(32);
+    else {
+        const int resident = T <= SC_RESIDENT ? 1 : 0;
+        const size_t smem = resident ? align_up((size_t)T * sizeof(double), 16) : 0;
+        cudaError_t e = ensure_dyn_smem(k_score_sensor, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "smem attribute k_score_sensor");
+        k_score_sensor<<<N, 256, smem, st>>>(dT, T, resident, stats, scores, top1);
     }
+#undef SC_LAUNCH_REG
+#undef SC_LAUNCH_REG2
+    GDN_CHECK_LAUNCH("k_score_sensor");
     return 0;
 }
 

@@ -7,11 +7,48 @@ wraps any iterable of `(x, y, ...)` CPU batches -- e.g. the reference's DataLoad
 an event per batch, and the consumer stream waits on that event only.  Tensors whose name position is
 listed in `skip` (default: the 4th, `edge_index`) are passed through untouched.
 """
+import queue
+import threading
+
 import torch
 
 
+class LossReader:
+    """train.py:76-77 reads `loss.item()` after every step: a device synchronisation per step, which serialises the
+    host side of step k+1 (feed, launches) behind the device side of step k.  This reader keeps the read -- 4 bytes
+    device -> pinned host every step -- but hands the value back one step late: `push(loss)` enqueues the copy of
+    step k and returns the value of step k-1 (already on the host by then), `flush()` returns what is still in
+    flight.  The sequence of values is exactly what `.item()` per step would have produced."""
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.depth = int(depth)
+        self.host = torch.zeros(self.depth, dtype=torch.float32, pin_memory=True)
+        self.events = [None] * self.depth
+        self.count = 0
+
+    def _take(self, k):
+        self.events[k % self.depth].synchronize()
+        return float(self.host[k % self.depth])
+
+    def push(self, loss):
+        k = self.count
+        out = self._take(k - self.depth + 1) if k >= self.depth - 1 else None     # the oldest value still in flight
+        slot = k % self.depth
+        self.host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.events[slot] = ev
+        self.count += 1
+        return out
+
+    def flush(self):
+        first = max(0, self.count - self.depth + 1)
+        return [self._take(k) for k in range(first, self.count)]
+
+
 class Prefetcher:
-    def __init__(self, batches, device, skip=(3,), dtype=torch.float32, reuse_buffers=False):
+    def __init__(self, batches, device, skip=(3,), dtype=torch.float32, reuse_buffers=False, threaded=False):
         """reuse_buffers=True copies into two persistent device buffers per tensor position (no allocator
         traffic); a yielded batch is then only valid until the NEXT-BUT-ONE batch is requested -- right
         for train.py's loop, wrong for a consumer that keeps aliases of its inputs (test.py:55-57 keeps the
@@ -23,6 +60,10 @@ class Prefetcher:
         self.skip = set(skip)
         self.dtype = dtype
         self.reuse = bool(reuse_buffers)
+        # threaded=True: staging (dtype cast into pinned memory: the reference's loader yields pageable float64,
+        # datasets/TimeDataset.py:64-73) and the H2D copy of the NEXT batches run on a worker thread, so they overlap
+        # the consumer's device work even when the consumer blocks on `loss.item()` every step
+        self.threaded = bool(threaded)
         self.stream = torch.cuda.Stream(device=self.device)
         self._pinned = {}
         self._devbuf = {}
@@ -83,7 +124,58 @@ class Prefetcher:
         self._copied[slot] = ev
         return out, ev
 
+    def _iter_threaded(self):
+        cur_stream = torch.cuda.current_stream(self.device)
+        free_q, ready_q = queue.Queue(), queue.Queue()
+        free_q.put((0, None))
+        free_q.put((1, None))
+        stop = threading.Event()
+
+        def work():
+            try:
+                torch.cuda.set_device(self.device)
+                for batch in self.batches:
+                    while True:
+                        try:
+                            slot, after = free_q.get(timeout=0.2)
+                            break
+                        except queue.Empty:
+                            if stop.is_set():
+                                return
+                    out, ev = self._issue(slot, batch, after)
+                    ready_q.put((slot, out, ev))
+                ready_q.put(None)
+            except BaseException as e:                      # surfaces in the consumer
+                ready_q.put(e)
+
+        th = threading.Thread(target=work, name="gdn-prefetch", daemon=True)
+        th.start()
+        try:
+            while True:
+                item = ready_q.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                slot, cur, ev = item
+                cur_stream.wait_event(ev)
+                if not self.reuse:
+                    for t in cur:
+                        if torch.is_tensor(t) and t.is_cuda:
+                            t.record_stream(cur_stream)
+                yield tuple(cur)
+                done = None
+                if self.reuse:
+                    done = torch.cuda.Event()
+                    done.record(cur_stream)
+                free_q.put((slot, done))
+        finally:
+            stop.set()
+
     def __iter__(self):
+        if self.threaded:
+            yield from self._iter_threaded()
+            return
         it = iter(self.batches)
         cur_stream = torch.cuda.current_stream(self.device)
         done = [None, None]

@@ -11,6 +11,8 @@ averaged.
 The host logic below is backend-agnostic (it runs under gloo on CPU in tests/test_dp_cpu.py);
 bench.py uses it with the nccl backend.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -74,15 +76,35 @@ class WindowShardedTrainer:
     """The reference's train step (train.py:68-73: zero_grad, forward, mse, backward, Adam
     step) on this rank's window shard, with the flat gradient all-reduce before the step."""
 
-    def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, shard_graph=None, flat_adam=False):
-        """flat_adam=True: parameters, gradients and Adam moments live in flat buffers
-        (`gdn_b200.optim.FlatAdam`); the all-reduce works on the gradient buffer in place and the 1/world scaling is
-        fused into the single Adam kernel.  Default: torch.optim.Adam (fused on CUDA) + FlatGradAllReduce."""
+    def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, shard_graph=None, flat_adam=None,
+                 nvls=None):
+        """flat_adam (default on CUDA): parameters, gradients and Adam moments live in flat buffers
+        (`gdn_b200.optim.FlatAdam`): autograd accumulates straight into the buffer the all-reduce works on, and the
+        1/world scaling is fused into the single Adam kernel -- no `torch.cat`, no `mul_`, no re-pointing of `.grad`
+        per step.  flat_adam=False: torch.optim.Adam (fused on CUDA) + FlatGradAllReduce (the CPU / gloo path).
+        nvls (default: when the group's GPUs expose NVLink multicast): the all-reduce, the update and the broadcast of
+        the new parameters run as ONE kernel over NVSwitch multicast memory (`gdn_b200.optim.NvlsFlatAdam`)."""
         self.model = model
         self.group = group
         params = list(model.parameters())
         self.flat = None
-        if flat_adam:
+        if flat_adam is None:
+            flat_adam = bool(params) and all(p.is_cuda and p.dtype == torch.float32 for p in params)
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if flat_adam and nvls is None:
+            nvls = world > 1 and os.environ.get("GDN_NVLS", "1") != "0"
+        self.nvls = None
+        if flat_adam and nvls and world > 1:
+            from .optim import NvlsFlatAdam
+            try:
+                self.nvls = NvlsFlatAdam(params, lr=lr, weight_decay=weight_decay, group=group)
+            except NvlsFlatAdam.Unavailable as e:          # no multicast on this box / torch build: NCCL path below
+                self.nvls_unavailable = str(e)
+        if self.nvls is not None:
+            self.flat = self.nvls
+            self.opt = self.nvls
+            self.reduce = None
+        elif flat_adam:
             from .optim import FlatAdam
             self.flat = FlatAdam(params, lr=lr, weight_decay=weight_decay)
             self.opt = self.flat
@@ -104,6 +126,13 @@ class WindowShardedTrainer:
             model.shard_graph_build(dist.get_rank(group), dist.get_world_size(group), group)
 
     def step(self, x, y):
+        if self.nvls is not None:
+            self.nvls.zero_grad()
+            out = self.model(x, None)
+            loss = torch.nn.functional.mse_loss(out, y, reduction="mean")
+            loss.backward()
+            self.nvls.step()                       # all-reduce + Adam + parameter broadcast: one kernel
+            return loss
         if self.flat is not None:
             self.flat.zero_grad()
             out = self.model(x, None)
@@ -123,3 +152,94 @@ class WindowShardedTrainer:
         self.reduce()
         self.opt.step()
         return loss
+
+
+# ------------------------------------------------------------------------------------------------ evaluation
+def shard_loader_batches(n_batches, rank, world):
+    """Contiguous range [lo, hi) of a loader's batches evaluated by `rank` (test.py:43: batches are independent in
+    eval mode; contiguous so that every rank ends up with a contiguous range of ticks)."""
+    return shard_bounds(n_batches, rank, world)
+
+
+def sharded_test(model, dataloader, group=None):
+    """test.py:20-75 on `world` ranks ("Scoring: shards ... by window for the eval forward"): every rank runs
+    the eval forward on a contiguous slice of the loader's batches.  Returns (avg_loss over ALL ticks, pred_local
+    [T_r, N], gt_local [T_r, N], labels_local [T_r]) -- device tensors; the global average loss costs one all-reduce
+    of two doubles.  Feed the local tensors to `sharded_scores`."""
+    from .test import test as _test
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    batches = list(range(len(dataloader)))
+    lo, hi = shard_loader_batches(len(batches), rank, world)
+
+    class _Slice:
+        def __init__(self, inner):
+            self.inner = inner
+
+        def __iter__(self):
+            for k, b in enumerate(self.inner):
+                if k >= hi:
+                    break
+                if k >= lo:
+                    yield b
+
+    dev = next(model.parameters()).device
+    if hi > lo:
+        loss, res = _test(model, _Slice(dataloader))
+        pred, gt, lab = res.device_tensors
+        n_batches = hi - lo
+    else:                                                       # more ranks than batches
+        N = model.embedding.num_embeddings
+        loss, n_batches = 0.0, 0
+        pred = torch.empty((0, N), dtype=torch.float32, device=dev)
+        gt, lab = torch.empty_like(pred), torch.empty((0, N), dtype=torch.float32, device=dev)
+    acc = torch.tensor([loss * n_batches, float(n_batches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(acc, group=group)
+    return float(acc[0].item() / max(acc[1].item(), 1.0)), pred, gt, lab[:, 0] if lab.dim() == 2 else lab
+
+
+def sharded_scores(pred_local, gt_local, group=None, want_scores=True, score_fn=None):
+    """evaluate.py:6-36 + 134-139 on `world` ranks ("Scoring shards by sensor ... final gather of [T]
+    maxima").  Input: this rank's contiguous tick range [T_r, N] of predictions / ground truth (ranks in tick order,
+    as `sharded_test` leaves them).  The scorer needs whole series per sensor, so the one exchange step is an
+    all-to-all that turns the tick sharding into a sensor sharding ([T_r, N] -> [T, N_r], 8 T N / world bytes per
+    rank); every rank then scores its N_r sensors, and the per-tick maximum over sensors is one all-reduce(MAX) of
+    [T] doubles.  Returns (scores_local [N_r, T] float64 or None, top1 [T] float64 on every rank, (n_lo, n_hi))."""
+    from . import ops
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    if score_fn is None:
+        score_fn = lambda p, g: ops.score(p, g, want_scores=want_scores, want_top1=True)[:2]
+    T_r, N = pred_local.shape
+    dev = pred_local.device
+    if world == 1:
+        s, top1 = score_fn(pred_local.contiguous(), gt_local.contiguous())
+        return s, top1, (0, N)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    counts[rank] = T_r
+    dist.all_reduce(counts, group=group)
+    t_counts = [int(c) for c in counts.tolist()]
+    T = sum(t_counts)
+    cols = [shard_bounds(N, q, world) for q in range(world)]
+    n_lo, n_hi = cols[rank]
+    n_me = n_hi - n_lo
+    # send to rank q: (pred, gt)[my ticks, q's sensors]; receive from rank q: (pred, gt)[q's ticks, my sensors]
+    both = torch.stack([pred_local, gt_local])                                  # [2, T_r, N]
+    send = torch.cat([both[:, :, a:b].reshape(-1) for a, b in cols])
+    in_split = [2 * T_r * (b - a) for a, b in cols]
+    out_split = [2 * tq * n_me for tq in t_counts]
+    recv = torch.empty(sum(out_split), dtype=both.dtype, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split, group=group)
+    parts, off = [], 0
+    for tq, nb in zip(t_counts, out_split):
+        parts.append(recv[off:off + nb].view(2, tq, n_me))
+        off += nb
+    mine = torch.cat(parts, dim=1)                                              # [2, T, n_me]
+    if n_me > 0:
+        s, top1 = score_fn(mine[0].contiguous(), mine[1].contiguous())
+    else:
+        s = torch.empty((0, T), dtype=torch.float64, device=dev)
+        top1 = torch.full((T,), float("-inf"), dtype=torch.float64, device=dev)
+    dist.all_reduce(top1, op=dist.ReduceOp.MAX, group=group)
+    return s, top1, (n_lo, n_hi)

@@ -148,15 +148,15 @@ class GDN(nn.Module):
         rank, world, group = self._graph_shard
         N, K = w.shape[0], int(self.topk)
         r0, r1, chunk = graph_row_shard(N, rank, world)
-        idx = torch.empty((world * chunk, K), dtype=torch.int64, device=w.device)
         nbr = torch.empty((world * chunk, K + 1), dtype=torch.int32, device=w.device)
         if r1 > r0:
             ops.graph_build(w, K, use_tensor_cores=self.use_tensor_cores, kth=self._kth, margin=self.graph_margin,
-                            rows=(r0, r1), out=(idx, nbr))
-        # in-place all-gather: every rank's chunk sits at its own offset of the padded tables
+                            rows=(r0, r1), out=(None, nbr))
+        # ONE in-place all-gather of the int32 table (4 (K+1) bytes per sensor); the int64 learned_graph the API
+        # publishes is rebuilt locally from it (the table records where each row sat in its own top-k)
         dist.all_gather_into_tensor(nbr, nbr[rank * chunk:(rank + 1) * chunk], group=group)
-        dist.all_gather_into_tensor(idx, idx[rank * chunk:(rank + 1) * chunk], group=group)
-        return idx[:N], nbr[:N]
+        nbr = nbr[:N]
+        return ops.idx_from_nbr(nbr), nbr
 
     def build_graph(self):
         """models/GDN.py:143-159.  The reference rebuilds the graph in every forward; so do we in

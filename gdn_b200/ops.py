@@ -58,11 +58,12 @@ def graph_build(V, topk, use_tensor_cores=-1, want_idx=True, kth=None, margin=0.
     if not 1 <= K <= N:
         raise RuntimeError(f"topk={K} must be in 1..node_num={N} (torch.topk would raise too)")
     if out is not None:
-        idx, nbr = out
-        if idx.dtype != torch.int64 or nbr.dtype != torch.int32 or idx.shape[0] < N or nbr.shape[0] < N \
-                or tuple(idx.shape[1:]) != (K,) or tuple(nbr.shape[1:]) != (K + 1,) \
-                or not idx.is_contiguous() or not nbr.is_contiguous() or idx.device != Vc.device or nbr.device != Vc.device:
-            raise RuntimeError("out must be contiguous (int64 [>=N, K], int32 [>=N, K+1]) on the embedding's device")
+        idx, nbr = out                      # idx may be None: only the neighbour table is wanted
+        bad_idx = idx is not None and (idx.dtype != torch.int64 or idx.shape[0] < N or tuple(idx.shape[1:]) != (K,)
+                                       or not idx.is_contiguous() or idx.device != Vc.device)
+        if bad_idx or nbr.dtype != torch.int32 or nbr.shape[0] < N or tuple(nbr.shape[1:]) != (K + 1,) \
+                or not nbr.is_contiguous() or nbr.device != Vc.device:
+            raise RuntimeError("out must be contiguous (int64 [>=N, K] or None, int32 [>=N, K+1]) on the embedding's device")
     else:
         idx = torch.empty((N, K), dtype=torch.int64, device=Vc.device) if want_idx else None
         nbr = torch.empty((N, K + 1), dtype=torch.int32, device=Vc.device)
@@ -83,6 +84,21 @@ def graph_build(V, topk, use_tensor_cores=-1, want_idx=True, kth=None, margin=0.
                                        int(use_tensor_cores), ptr(kth), float(margin), _stream()),
               "gdn_graph_build_warm")
     return idx, nbr
+
+
+def idx_from_nbr(nbr):
+    """learned_graph [N, K] int64 from the neighbour table alone.  The table lists the row's non-self top-k entries
+    in order, then the row itself; when the row was in its own top-k (practically always: cos = 1) the last slot holds
+    -2 - (its position there), so the top-k order is recoverable.  Index plumbing (a gather over N*K ints) for the
+    data-parallel graph exchange: ranks all-gather the int32 table only and rebuild the int64 one locally."""
+    N, Kp = nbr.shape
+    K = Kp - 1
+    last = nbr[:, K].long()
+    pos = torch.where(last <= -2, -2 - last, torch.full_like(last, K))          # K: self not in the top-k / at the end
+    j = torch.arange(K, device=nbr.device).unsqueeze(0)
+    p = pos.unsqueeze(1)
+    col = torch.where(j < p, j, torch.where(j == p, torch.full_like(j, K - 1), j - 1))
+    return torch.gather(nbr[:, :K].long(), 1, col.expand(N, K) if col.shape[0] == 1 else col)
 
 
 # ----------------------------------------------------------------------------- GraphLayer, shared graph

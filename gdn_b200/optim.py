@@ -50,3 +50,90 @@ class FlatAdam:
         check(lib.gdn_adam_flat(ptr(self.flat), ptr(self.grad_buffer), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                                 self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                 self.step_count, float(grad_scale), torch.cuda.current_stream().cuda_stream), "gdn_adam_flat")
+
+
+class NvlsFlatAdam:
+    """The data-parallel optimiser step over NVSwitch multicast memory (SURVEY §8 row f-4 as written): gradient
+    all-reduce, Adam and the broadcast of the new parameters are ONE kernel (`gdn_nvls_adam`) instead of an NCCL
+    all-reduce followed by an update on every rank.
+
+    Plumbing (torch.distributed._symmetric_memory): the flat parameter and gradient buffers are symmetric allocations
+    bound to multicast objects; the module's Parameters (and their `.grad`s) are views of them.  Rank r owns a 1/G
+    slice: it pulls the switch-reduced gradient of that slice (`multimem.ld_reduce`), updates its slice of the Adam
+    moments -- the optimiser state is sharded G-fold -- and stores the new parameters to every replica
+    (`multimem.st`).  Two tiny cross-rank barriers (signal pads) bracket the kernel on the compute stream."""
+
+    class Unavailable(RuntimeError):
+        pass
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None):
+        import torch.distributed as dist
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise RuntimeError("NvlsFlatAdam: no parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in self.params):
+            raise RuntimeError("NvlsFlatAdam needs float32 parameters on one CUDA device (gdn_b200 has no CPU path)")
+        if not (dist.is_available() and dist.is_initialized()):
+            raise self.Unavailable("torch.distributed is not initialised")
+        try:
+            import torch.distributed._symmetric_memory as symm
+        except Exception as e:                                   # pragma: no cover
+            raise self.Unavailable(f"torch symmetric memory is not importable: {e}")
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        self.step_count = 0
+        n = sum(p.numel() for p in self.params)
+        unit = 4 * self.world                                     # every slice a whole number of 16-byte vectors
+        self.n, self.n_pad = n, -(-n // unit) * unit
+        self.slice = self.n_pad // self.world
+        self.lo = self.rank * self.slice
+        try:
+            if hasattr(symm, "enable_symm_mem_for_group"):
+                try:
+                    symm.enable_symm_mem_for_group(group.group_name)
+                except Exception:
+                    pass
+            self.flat = symm.empty(self.n_pad, dtype=torch.float32, device=dev)
+            self.grad_buffer = symm.empty(self.n_pad, dtype=torch.float32, device=dev)
+            self.h_param = symm.rendezvous(self.flat, group)
+            self.h_grad = symm.rendezvous(self.grad_buffer, group)
+            self.p_mc, self.g_mc = int(self.h_param.multicast_ptr), int(self.h_grad.multicast_ptr)
+        except Exception as e:
+            raise self.Unavailable(f"symmetric memory rendezvous failed: {type(e).__name__}: {e}")
+        if self.p_mc == 0 or self.g_mc == 0:
+            raise self.Unavailable("this box / driver exposes no NVLink multicast (multicast_ptr == 0)")
+        self.exp_avg = torch.zeros(self.slice, dtype=torch.float32, device=dev)       # this rank's slice only
+        self.exp_avg_sq = torch.zeros(self.slice, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            self.flat.zero_()
+            self.grad_buffer.zero_()
+            for p in self.params:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat[off:off + k].view_as(p)
+                p.grad = self.grad_buffer[off:off + k].view_as(p)
+                off += k
+        torch.cuda.synchronize(dev)
+        self.h_param.barrier(channel=0)
+
+    def zero_grad(self):
+        self.grad_buffer.zero_()
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.grad_buffer.data_ptr() + 4 * off:
+                p.grad = self.grad_buffer[off:off + k].view_as(p)
+            off += k
+
+    def step(self, grad_scale=None):
+        lib = _lib.load()
+        self.step_count += 1
+        scale = 1.0 / self.world if grad_scale is None else float(grad_scale)
+        self.h_grad.barrier(channel=0)                            # every rank's backward has written its gradients
+        check(lib.gdn_nvls_adam(ptr(self.flat), self.p_mc, self.g_mc, ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                self.lo, self.slice, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                self.step_count, scale, torch.cuda.current_stream().cuda_stream), "gdn_nvls_adam")
+        self.h_param.barrier(channel=1)                           # every slice of the new parameters has landed

@@ -18,6 +18,8 @@
  *                          util/data.py:28-51 (eval_scores) and evaluate.py:129-158
  *                          (get_best_performance_data): threshold sweep / F1, precision, recall, AUC
  *   gdn_adam_flat          train.py:31,73 (torch.optim.Adam step) on flat buffers, 1/G gradient scaling fused
+ *   gdn_nvls_adam          the same step on G ranks: gradient all-reduce + Adam + parameter broadcast, one kernel
+ *                          over NVSwitch multicast memory
  *   gdn_window_batch       datasets/TimeDataset.py:33-62 (+ the per-step transfer train.py:66):
  *                          window batches gathered from a device-resident series
  *
@@ -132,7 +134,9 @@ int gdn_profile_collect(char* buf, size_t buf_bytes);
  *          by bench.py);
  *          and nbr [N, K+1] int32: the neighbour list GraphLayer actually uses after
  *          remove_self_loops/add_self_loops (models/graph_layer.py:61-63): the non-self
- *          top-k entries in order, then the sensor itself, then -1 padding.
+ *          top-k entries in order, then the sensor itself, then negative padding (any negative value ends
+ *          the list; when the sensor was in its own top-k the LAST slot holds -2 - its position there, the
+ *          other padding slots -1, so idx is recoverable from nbr alone).
  * Either output may be NULL.  use_tensor_cores: 0 = exact fp32 CUDA-core Gram,
  * 1 = tcgen05 split-precision Gram with exact fp32 re-scoring, -1 = choose by N. */
 size_t gdn_graph_build_ws_bytes(int N, int D, int K);
@@ -216,6 +220,15 @@ int    gdn_score(const float* pred, const float* gt, int T, int N, double* score
 int    gdn_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                      float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale,
                      void* stream);
+/* Data-parallel step over NVSwitch multicast memory (train.py:73 on G ranks): all-reduce of the flat gradient,
+ * Adam and the broadcast of the new parameters in one kernel.  params_mc / grads_mc are the MULTICAST addresses of
+ * the symmetric flat parameter / gradient buffers (every rank's replica bound to one multicast object, e.g. through
+ * torch.distributed._symmetric_memory); params_local is this rank's replica.  This rank owns elements
+ * [lo, lo + count) (both multiples of 4) and holds Adam moments for that slice only (exp_avg, exp_avg_sq: `count`
+ * floats).  The caller brackets the call with cross-rank barriers on the same stream. */
+int    gdn_nvls_adam(const float* params_local, float* params_mc, const float* grads_mc, float* exp_avg,
+                     float* exp_avg_sq, long long lo, long long count, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, long long step, float grad_scale, void* stream);
 
 /* ---- evaluation metrics (util/data.py:28-51, evaluate.py:129-158) ----
  * sorted_scores [T] float64 ascending (stable), labels_sorted [T] float32 in {0,1} in the same order.

@@ -118,10 +118,14 @@ def _cpu_graph_rows(V, topk, use_tensor_cores=-1, want_idx=True, kth=None, margi
     idx = torch.topk(Vn[r0:r1] @ Vn.t(), K, dim=1).indices
     nbr = torch.full((r1 - r0, K + 1), -1, dtype=torch.int32)
     for a in range(r1 - r0):
-        keep = [int(j) for j in idx[a] if int(j) != r0 + a] + [r0 + a]
+        row = [int(j) for j in idx[a]]
+        keep = [j for j in row if j != r0 + a] + [r0 + a]
         nbr[a, :len(keep)] = torch.tensor(keep, dtype=torch.int32)
+        if r0 + a in row:                                       # include/gdn_b200.h: last slot = -2 - position of self
+            nbr[a, K] = -2 - row.index(r0 + a)
     full_idx, full_nbr = out
-    full_idx[r0:r1] = idx
+    if full_idx is not None:
+        full_idx[r0:r1] = idx
     full_nbr[r0:r1] = nbr
     return full_idx, full_nbr
 
@@ -165,4 +169,63 @@ def test_row_sharded_graph_build_world2_gloo():
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_graph_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert len(ret) == world
+
+
+def test_idx_from_nbr_rebuilds_the_topk_order():
+    """The data-parallel exchange ships the int32 neighbour table only; learned_graph is rebuilt from it.  Self first
+    (the usual case), self in the middle, self last, self absent."""
+    from gdn_b200 import ops
+    N, K = 9, 4
+    idx = torch.tensor([[0, 3, 5, 7], [2, 1, 4, 6], [8, 7, 6, 2], [1, 2, 4, 5], [4, 0, 1, 2],
+                        [0, 1, 5, 2], [6, 1, 2, 3], [0, 7, 2, 3], [1, 2, 3, 8]], dtype=torch.int64)
+    full = (torch.empty(N, K, dtype=torch.int64), torch.empty(N, K + 1, dtype=torch.int32))
+    nbr = torch.full((N, K + 1), -1, dtype=torch.int32)
+    for i in range(N):
+        row = [int(j) for j in idx[i]]
+        keep = [j for j in row if j != i] + [i]
+        nbr[i, :len(keep)] = torch.tensor(keep, dtype=torch.int32)
+        if i in row:
+            nbr[i, K] = -2 - row.index(i)
+    assert int(nbr[3, K]) == 3                                  # self absent: K non-self entries, then self
+    assert torch.equal(ops.idx_from_nbr(nbr), idx)
+
+
+def _score_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from gdn_b200.dp import shard_bounds, sharded_scores
+        from oracle import scoring_oracle as so
+        rng = np.random.default_rng(7)
+        T, N = 53, 7                                            # neither divides by the world size
+        gt = rng.random((T, N)).astype(np.float32)
+        pred = (gt + rng.normal(0, 0.05, (T, N))).astype(np.float32)
+
+        def cpu_scorer(p, g):                                   # stand-in for ops.score (CUDA only), same contract
+            s = so.full_err_scores(p.numpy(), g.numpy())
+            return torch.from_numpy(s), torch.from_numpy(s.max(axis=0))
+
+        lo, hi = shard_bounds(T, rank, world)
+        s, top1, (n_lo, n_hi) = sharded_scores(torch.from_numpy(pred[lo:hi]), torch.from_numpy(gt[lo:hi]),
+                                               score_fn=cpu_scorer)
+        ref = so.full_err_scores(pred, gt)
+        assert (n_lo, n_hi) == shard_bounds(N, rank, world)
+        assert np.array_equal(s.numpy(), ref[n_lo:n_hi])
+        assert np.array_equal(top1.numpy(), ref.max(axis=0))
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_scoring_gloo(world):
+    """SURVEY section 8e / row e-2 on CPU: ticks sharded over ranks -> all-to-all -> sensors sharded -> scores of the
+    local sensors + all-reduce(MAX) of the per-tick maximum; equals the single-process scorer bit for bit."""
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_score_worker, args=(world, port, ret), nprocs=world, join=True)
         assert len(ret) == world
