@@ -259,6 +259,94 @@ def graphlayer_bytes(wl):
     return fwd, bwd
 
 
+def dp_gradient_check(dev, rank, world):
+    """Numerical check of the data-parallel step on the real model over NCCL (every rank takes part): the summed
+    gradient buffer / world must equal the average of the float64 oracle's per-shard gradients (results
+    equal the reference evaluated on each rank's shard with averaged gradients), and the NVLS one-kernel step must
+    leave the same parameters as the NCCL all-reduce + flat Adam step."""
+    import torch
+    import torch.distributed as dist
+    from gdn_b200.dp import WindowShardedTrainer
+    from gdn_b200.models.GDN import GDN
+    from oracle import gdn_oracle as go
+    N, W, D, K, Bc = 127, 5, 128, 30, 8
+    sd = go.init_state(N, D, W, seed=5, stressed=True)
+    g = torch.Generator().manual_seed(100 + rank)
+    x, y = torch.rand(Bc, N, W, generator=g), torch.rand(Bc, N, generator=g)
+    mask = go.dropout_mask(Bc, N, D, seed=50 + rank)
+
+    def make(nvls):
+        m = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K)
+        m.load_state_dict(sd)
+        m = m.to(dev).train()
+        m.set_dropout_mask(mask.to(dev))
+        return m, WindowShardedTrainer(m, lr=1e-3, flat_adam=True, nvls=nvls)
+
+    out = {}
+    model, tr = make(False)
+    names = [k for k, _ in model.named_parameters()]
+    tr.step(x.to(dev), y.to(dev))
+    summed = tr.flat.grad_buffer.detach().clone()                 # NCCL all-reduced in place (sum); 1/world is in the Adam kernel
+    _, _, g64, _ = go.loss_and_grads(go.cast_state(sd, torch.float64), x.double(), y.double(), K, drop_mask=mask.double())
+    ref = torch.cat([g64[k].reshape(-1) for k in names]).to(dev)
+    dist.all_reduce(ref)
+    ref /= world
+    err, off = 0.0, 0
+    for k, p in model.named_parameters():
+        n = p.numel()
+        if not k.endswith("gnn.bias"):                            # analytically zero gradient: pure rounding noise
+            a, b = summed[off:off + n].double() / world, ref[off:off + n]
+            err = max(err, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+        off += n
+    out["grad_max_normwise_err_vs_oracle_f64"] = err
+    out["grad_pass"] = err < 1e-4
+    p_nccl = tr.flat.flat.detach().clone()
+    for _ in range(2):
+        tr.step(x.to(dev), y.to(dev))
+    p_nccl3 = tr.flat.flat.detach().clone()
+    model2, tr2 = make(True)
+    if tr2.nvls is None:
+        out["nvls"] = "unavailable: " + getattr(tr2, "nvls_unavailable", "not requested")
+    else:
+        for _ in range(3):
+            tr2.step(x.to(dev), y.to(dev))
+        n = p_nccl3.numel()
+        d = (tr2.nvls.flat[:n] - p_nccl3).abs().max() / p_nccl3.abs().max()
+        out["nvls_vs_nccl_param_err_after_3_steps"] = float(d)
+        mine = tr2.nvls.flat.detach().clone()
+        ref0 = mine.clone()
+        dist.broadcast(ref0, 0)
+        out["nvls_replicas_bit_identical"] = bool(torch.equal(mine, ref0))
+        out["nvls_pass"] = float(d) < 1e-5 and out["nvls_replicas_bit_identical"]
+    flag = torch.tensor([1.0 if all(v for k, v in out.items() if k.endswith("pass")) else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["pass_all_ranks"] = bool(flag.item() > 0)
+    return out
+
+
+def sharded_score_leg(model, xs, dev, rank, world, B, N, flush, timed_max):
+    """Row e-2: the score path on `world` GPUs.  Eval forward: every rank evaluates its own B windows per step;
+    scoring: T ticks sharded over ranks -> all-to-all -> per-sensor scoring of N/world sensors -> all-reduce(MAX)."""
+    import torch
+    from gdn_b200.dp import shard_bounds, sharded_scores
+    model.eval()
+    T = 4096
+    lo, hi = shard_bounds(T, rank, world)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    pl, gl = torch.rand(hi - lo, N, device=dev, generator=g), torch.rand(hi - lo, N, device=dev, generator=g)
+    with torch.no_grad():
+        ev = timed_max(lambda i: model(xs[i % len(xs)], None), 5, 3)
+        sc = timed_max(lambda i: sharded_scores(pl, gl, want_scores=True), 5, 2)
+    model.train()
+    ev_wps = world * B / (ev * 1e-3)
+    sc_tps = T / (sc * 1e-3)
+    return {"n_gpus": world, "eval_forward_windows_per_s": ev_wps, "scoring_ticks_per_s": sc_tps,
+            "score_windows_per_s": 1.0 / (1.0 / ev_wps + 1.0 / sc_tps), "scoring_T": T,
+            "scoring_ms": sc, "eval_forward_ms": ev,
+            "what": "eval forward of B windows per rank (window-sharded); scoring of T ticks x N sensors: tick-sharded "
+                    "inputs -> all-to-all (NCCL) -> sensor-sharded gdn_score -> all-reduce(MAX) of the per-tick maximum"}
+
+
 # --------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -396,6 +484,27 @@ def run_ours(args):
         del hx, hy
     clocks = sampler.stop() if rank == 0 else None
 
+    dp_info = score_multi = None
+    if world > 1 and not args.no_extras:
+        def timed_max(fn, reps, warm):
+            for i in range(warm):
+                fn(i)
+            ms = []
+            for i in range(reps):
+                barrier()
+                flush.fill_(i & 0xFF)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn(i)
+                b_.record()
+                torch.cuda.synchronize()
+                ms.append(a.elapsed_time(b_))
+            t = torch.tensor([statistics.mean(ms)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        score_multi = sharded_score_leg(model, xs, dev, rank, world, B, N, flush, timed_max)
+        dp_info = dp_gradient_check(dev, rank, world)
+
     # ---- the same step captured into a CUDA graph (single GPU): what the launch-bound configs gain
     graph_info = None
     if world == 1 and not args.no_extras:
@@ -462,6 +571,15 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,
     }
+    if dp_info is not None:
+        line["dp_check"] = dp_info
+    if score_multi is not None:
+        line["score"] = score_multi
+    if world > 1:
+        line["optimizer_step"] = ("gdn_nvls_adam: all-reduce + Adam + parameter broadcast in one kernel over NVSwitch multicast"
+                                  if trainer.nvls is not None else
+                                  "NCCL all-reduce of the flat gradient buffer + gdn_adam_flat" + (
+                                      " (NVLS unavailable: " + getattr(trainer, "nvls_unavailable", "") + ")" if hasattr(trainer, "nvls_unavailable") else ""))
     if graph_info is not None:
         line["cuda_graph"] = graph_info
     if feed_info is not None:
@@ -513,16 +631,21 @@ def run_ours(args):
         fb, bb = graphlayer_bytes(wl)
         f_ms, b_ms = statistics.mean(fwd_ms), statistics.mean(bwd_ms)
         achieved = (fb + bb) / ((f_ms + b_ms) * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_file = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[name]["graphlayer_fwd_bwd_dram_bytes"]
+            for tf in ("r02_traffic.json", "r01_traffic.json"):
+                tp_ = os.path.join(ROOT, "profiles", tf)
+                if os.path.exists(tp_):
+                    traffic = json.load(open(tp_))[name]["graphlayer_fwd_bwd_dram_bytes"]
+                    traffic_file = tf
+                    break
         except Exception:
             pass
         line["roofline"] = {
             "kernel": "GraphLayer fwd+bwd at the module boundary (gdn_graphlayer_fwd + gdn_graphlayer_bwd)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full: dram__bytes_read.sum + "
-            "dram__bytes_write.sum over the 13 kernels of one fwd+bwd)" if traffic else None,
+            "traffic": traffic, "traffic_source": f"profiles/{traffic_file} (ncu --set full: dram__bytes_read.sum + "
+            "dram__bytes_write.sum over the kernels of one fwd+bwd)" if traffic else None,
             "peak_source": peak_src, "algorithmic_bytes": fb + bb,
             "fwd_ms": f_ms, "bwd_ms": b_ms,
             "fwd_frac": fb / (f_ms * 1e-3) / 1e9 / peak, "bwd_frac": bb / (b_ms * 1e-3) / 1e9 / peak,
@@ -545,14 +668,21 @@ def run_ours(args):
             sc_pred = torch.rand(T, N, device=dev)
             sc_gt = torch.rand(T, N, device=dev)
             sc_ms = []
-            for i in range(6):
+            for i in range(8):
+                flush.fill_(i)
                 a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 ops.score(sc_pred, sc_gt)
                 b_.record()
                 torch.cuda.synchronize()
-                if i >= 2:
+                if i >= 3:
                     sc_ms.append(a.elapsed_time(b_))
+            lib.gdn_profile_enable(1)
+            for i in range(3):
+                ops.score(sc_pred, sc_gt)
+            torch.cuda.synchronize()
+            _, sc_rows = profile_collect(lib)
+            lib.gdn_profile_enable(0)
         # ---- summary metrics: 400-step F1 sweep + precision/recall/AUC over the SWaT length
         import time as _time
         from gdn_b200.evaluate import get_best_performance_data
@@ -580,11 +710,29 @@ def run_ours(args):
         model.train()
         ev_wps = B / (statistics.mean(ev_ms) * 1e-3)
         sc_wps = T / (statistics.mean(sc_ms) * 1e-3)
-        line["score"] = {"eval_forward_windows_per_s": ev_wps, "scoring_ticks_per_s": sc_wps,
-                         "score_windows_per_s": 1.0 / (1.0 / ev_wps + 1.0 / sc_wps), "scoring_T": T}
+        sc_bytes = 2 * 4 * N * T + 8 * N * T                     # pred + gt in (fp32), scores out (fp64)
+        sc_s = statistics.mean(sc_ms) * 1e-3
+        sc_block = {"eval_forward_windows_per_s": ev_wps, "scoring_ticks_per_s": sc_wps,
+                         "score_windows_per_s": 1.0 / (1.0 / ev_wps + 1.0 / sc_wps), "scoring_T": T,
+                         "roofline": {"kernel": "gdn_score (k_delta_transpose + k_score_sensor)", "bound": "hbm",
+                                      "algorithmic_bytes": sc_bytes, "ms": sc_s * 1e3, "achieved": sc_bytes / sc_s / 1e9,
+                                      "peak": peak, "unit": "GB/s", "frac": sc_bytes / sc_s / 1e9 / peak,
+                                      "kernels_ms": {k: round(t / c, 5) for k, (c, t) in sc_rows.items()}}}
+        if world == 1:
+            line["score"] = sc_block
+        else:
+            line["score"]["single_gpu"] = sc_block
         line["metrics"] = metrics_info
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_train_baseline(name, wl, args.cpu_budget_s)
+            # the checker's verdict on the graph this run trains on (SURVEY 8c top-k protocol, oracle/topk_protocol.py)
+            from oracle import topk_protocol as _tp
+            with torch.no_grad():
+                Vg = model.embedding.weight.detach()
+                idx_now, _ = ops.graph_build(Vg, K)
+            line["parity"] = {"topk_protocol": _tp.compare_topk(_tp.reference_cosines(Vg.cpu()), idx_now.cpu(), K),
+                              "what": "learned graph of the model as trained by this run vs torch.topk of the reference's "
+                                      "cosine matrix on the host: clean rows bit-exact, tie-affected rows canonical"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -73,17 +73,18 @@ class Prefetcher:
         return len(self.batches)
 
     def _stage(self, slot, pos, t):
-        """Pinned staging copy of a CPU tensor (re-used buffers, one set per slot)."""
+        """Pinned staging copy of a CPU tensor (re-used buffers, one set per slot).  A floating-point tensor of another
+        dtype (the reference's loader yields float64) is converted BY the copy into the pinned buffer: one pass over
+        the data, no intermediate tensor."""
         if t.is_cuda:
             return t
-        if t.is_floating_point() and t.dtype != self.dtype:
-            t = t.to(self.dtype)
-        if t.is_pinned():
+        want = self.dtype if (t.is_floating_point() and t.dtype != self.dtype) else t.dtype
+        if t.is_pinned() and want == t.dtype:
             return t
-        key = (slot, pos, tuple(t.shape), t.dtype)
+        key = (slot, pos, tuple(t.shape), want)
         buf = self._pinned.get(key)
         if buf is None:
-            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf = torch.empty(t.shape, dtype=want, pin_memory=True)
             self._pinned[key] = buf
         else:
             # the slot's previous H2D copy out of this buffer is only stream-ordered; a consumer without a
