@@ -71,6 +71,8 @@ SIGNATURES = {
     "gdn_score": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_size_t, c_fp]),
     "gdn_adam_flat": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_longlong, C.c_float, c_fp]),
+    "gdn_adam_flat_dev": (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    c_fp, C.c_float, c_fp]),
     "gdn_nvls_adam": (C.c_int, [c_fp, c_fp, c_fp, c_fp, c_fp, C.c_longlong, C.c_longlong, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_longlong, C.c_float, c_fp]),
     "gdn_f1_sweep": (C.c_int, [c_fp, c_fp, C.c_int, c_fp, c_fp, C.c_int, c_fp, c_fp, c_fp]),

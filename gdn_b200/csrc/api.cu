@@ -458,8 +458,19 @@ int gdn_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_
     GDN_CHECK_ARG(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && lr >= 0.f,
                   "adam_flat: bad hyper-parameters (step=%lld)", step);
     prof_enter((cudaStream_t)stream, "@adam_flat");
-    return launch_adam_flat(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
-                            (cudaStream_t)stream);
+    return launch_adam_flat(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, nullptr,
+                            grad_scale, (cudaStream_t)stream);
+}
+
+int gdn_adam_flat_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, const long long* step_dev, float grad_scale,
+                      void* stream) {
+    GDN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && step_dev && n >= 1, "adam_flat_dev: bad argument");
+    GDN_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && lr >= 0.f,
+                  "adam_flat_dev: bad hyper-parameters");
+    prof_enter((cudaStream_t)stream, "@adam_flat");
+    return launch_adam_flat(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, 0, step_dev,
+                            grad_scale, (cudaStream_t)stream);
 }
 
 int gdn_nvls_adam(const float* params_local, float* params_mc, const float* grads_mc, float* exp_avg, float* exp_avg_sq,

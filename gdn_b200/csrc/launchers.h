@@ -69,7 +69,8 @@ int launch_graph_build(const float* V, int N, int D, int K, int row0, int row1, 
 // scoring.cu
 // optim.cu
 int launch_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                     float eps, float weight_decay, long long step, float grad_scale, cudaStream_t st);
+                     float eps, float weight_decay, long long step, const long long* step_dev, float grad_scale,
+                     cudaStream_t st);
 
 int launch_nvls_adam(const float* p_local, float* p_mc, const float* g_mc, float* m, float* v, long long lo, long long cnt,
                      float lr, float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale,

@@ -12,10 +12,23 @@
 
 namespace gdn {
 
+// step_dev != NULL: the step count lives on the device (incremented by the caller on the same stream) and the bias
+// corrections are derived from it here -- a captured CUDA graph then advances Adam's step on every replay
 __global__ void __launch_bounds__(256)
 k_adam_flat(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
             float lr_over_bc1, float inv_sqrt_bc2, float beta1, float beta2, float eps, float weight_decay,
-            float grad_scale) {
+            float grad_scale, const long long* __restrict__ step_dev, float lr) {
+    if (step_dev != nullptr) {
+        __shared__ float bc[2];
+        if (threadIdx.x == 0) {
+            const double step = (double)*step_dev;
+            bc[0] = (float)((double)lr / (1.0 - pow((double)beta1, step)));
+            bc[1] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, step)));
+        }
+        __syncthreads();
+        lr_over_bc1 = bc[0];
+        inv_sqrt_bc2 = bc[1];
+    }
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float pi = p[i];
@@ -94,13 +107,15 @@ int launch_nvls_adam(const float* p_local, float* p_mc, const float* g_mc, float
 }
 
 int launch_adam_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                     float eps, float weight_decay, long long step, float grad_scale, cudaStream_t st) {
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+                     float eps, float weight_decay, long long step, const long long* step_dev, float grad_scale,
+                     cudaStream_t st) {
+    const double sh = (double)(step >= 1 ? step : 1);
+    const double bc1 = 1.0 - pow((double)beta1, sh), bc2 = 1.0 - pow((double)beta2, sh);
     long long gsz = (n + 255) / 256;
     if (gsz > 8LL * num_sms()) gsz = 8LL * num_sms();
     if (gsz < 1) gsz = 1;
     k_adam_flat<<<(int)gsz, 256, 0, st>>>(p, g, m, v, n, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), beta1, beta2, eps,
-                                          weight_decay, grad_scale);
+                                          weight_decay, grad_scale, step_dev, lr);
     GDN_CHECK_LAUNCH("k_adam_flat");
     return 0;
 }

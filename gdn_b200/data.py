@@ -48,7 +48,8 @@ class LossReader:
 
 
 class Prefetcher:
-    def __init__(self, batches, device, skip=(3,), dtype=torch.float32, reuse_buffers=False, threaded=False):
+    def __init__(self, batches, device, skip=(3,), dtype=torch.float32, reuse_buffers=False, threaded=False,
+                 stage_threads=1):
         """reuse_buffers=True copies into two persistent device buffers per tensor position (no allocator
         traffic); a yielded batch is then only valid until the NEXT-BUT-ONE batch is requested -- right
         for train.py's loop, wrong for a consumer that keeps aliases of its inputs (test.py:55-57 keeps the
@@ -64,6 +65,12 @@ class Prefetcher:
         # datasets/TimeDataset.py:64-73) and the H2D copy of the NEXT batches run on a worker thread, so they overlap
         # the consumer's device work even when the consumer blocks on `loss.item()` every step
         self.threaded = bool(threaded)
+        # stage_threads > 1: make sure torch's intra-op pool (which splits the staging copy and its dtype cast) has at
+        # least that many threads -- torch.distributed.run pins OMP_NUM_THREADS=1 per rank, which would leave a single
+        # thread to convert ~140 MB per step at the largest config
+        self.stage_threads = max(1, int(stage_threads))
+        if self.stage_threads > torch.get_num_threads():
+            torch.set_num_threads(self.stage_threads)
         self.stream = torch.cuda.Stream(device=self.device)
         self._pinned = {}
         self._devbuf = {}
@@ -92,7 +99,7 @@ class Prefetcher:
             ev = self._copied.get(slot)
             if ev is not None:
                 ev.synchronize()
-        buf.copy_(t)
+        buf.copy_(t)                                # converts while copying; split over torch's intra-op threads
         return buf
 
     def _to_device(self, slot, pos, h):

@@ -76,14 +76,20 @@ class WindowShardedTrainer:
     """The reference's train step (train.py:68-73: zero_grad, forward, mse, backward, Adam
     step) on this rank's window shard, with the flat gradient all-reduce before the step."""
 
+    GRAPH_MAX_ELEMS = 1 << 21          # batches up to this many input values are replayed from a CUDA graph
+
     def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, shard_graph=None, flat_adam=None,
-                 nvls=None):
+                 nvls=None, cuda_graph=None):
         """flat_adam (default on CUDA): parameters, gradients and Adam moments live in flat buffers
         (`gdn_b200.optim.FlatAdam`): autograd accumulates straight into the buffer the all-reduce works on, and the
         1/world scaling is fused into the single Adam kernel -- no `torch.cat`, no `mul_`, no re-pointing of `.grad`
         per step.  flat_adam=False: torch.optim.Adam (fused on CUDA) + FlatGradAllReduce (the CPU / gloo path).
         nvls (default: when the group's GPUs expose NVLink multicast): the all-reduce, the update and the broadcast of
-        the new parameters run as ONE kernel over NVSwitch multicast memory (`gdn_b200.optim.NvlsFlatAdam`)."""
+        the new parameters run as ONE kernel over NVSwitch multicast memory (`gdn_b200.optim.NvlsFlatAdam`).
+        cuda_graph (default: single process, flat Adam): the BASELINE configs with 27-127 sensors are launch-bound
+        (~25 launches for a few hundred microseconds of device work), so after two eager steps on a batch shape the
+        whole step -- graph build, forward, MSE, backward, Adam -- is captured once and replayed for every further
+        batch of that shape (other shapes, e.g. a short last batch, run eagerly on the same optimiser state)."""
         self.model = model
         self.group = group
         params = list(model.parameters())
@@ -117,6 +123,10 @@ class WindowShardedTrainer:
                 kw["fused"] = True
             self.opt = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, **kw)
             self.reduce = FlatGradAllReduce(params, group)
+        if cuda_graph is None:
+            cuda_graph = os.environ.get("GDN_CUDA_GRAPH", "1") != "0"
+        self.cuda_graph = bool(cuda_graph) and self.flat is not None and self.nvls is None and world == 1
+        self._graphs, self._seen, self._drop_counter = {}, {}, None
         # the graph depends on the (replicated) embedding only: every rank builds 1/world of its rows and the
         # neighbour tables are all-gathered (the one exchange step of the forward; off for a single process)
         if shard_graph is None:
@@ -125,7 +135,59 @@ class WindowShardedTrainer:
         if shard_graph:
             model.shard_graph_build(dist.get_rank(group), dist.get_world_size(group), group)
 
+    # ---------------------------------------------------------------- CUDA-graph replay of the step (fixed shapes)
+    def _flat_body(self, x, y):
+        self.flat.zero_grad()
+        out = self.model(x, None)
+        loss = torch.nn.functional.mse_loss(out, y, reduction="mean")
+        loss.backward()
+        self.flat.step(grad_scale=1.0)
+        return loss
+
+    def _capture(self, key, x, y):
+        from . import ops
+        dev = x.device
+        if self._drop_counter is None:
+            self._drop_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        xs, ys = torch.empty_like(x), torch.empty_like(y)
+        graph = torch.cuda.CUDAGraph()
+        was_training = self.model.training
+        self.model.train()
+        ops.set_dropout_counter(self._drop_counter)          # the Philox offset is read from a counter the graph bumps
+        try:
+            with torch.cuda.graph(graph):
+                self._drop_counter.add_(1)
+                loss = self._flat_body(xs, ys)
+        finally:
+            ops.set_dropout_counter(None)
+            self.model.train(was_training)
+        self._graphs[key] = (graph, xs, ys, loss)
+
+    def _graph_step(self, x, y):
+        key = (tuple(x.shape), tuple(y.shape), x.dtype, y.dtype, str(x.device))
+        entry = self._graphs.get(key)
+        if entry is None:
+            seen = self._seen.get(key, 0)
+            if seen < 2 or not self.model.training:           # lazy initialisations happen in eager steps
+                self._seen[key] = seen + 1
+                return None
+            self._capture(key, x, y)
+            entry = self._graphs[key]
+        graph, xs, ys, loss = entry
+        xs.copy_(x, non_blocking=True)
+        ys.copy_(y, non_blocking=True)
+        graph.replay()
+        # the replay moves embedding.weight without touching its version counter: drop any eval-mode graph cache
+        self.model._graph_cache = None
+        return loss
+
     def step(self, x, y):
+        if self.cuda_graph and x.is_cuda and y.is_cuda and x.dtype == torch.float32 and y.dtype == torch.float32 \
+                and x.numel() <= self.GRAPH_MAX_ELEMS and x.is_contiguous() and y.is_contiguous() \
+                and not torch.cuda.is_current_stream_capturing():
+            loss = self._graph_step(x, y)
+            if loss is not None:
+                return loss
         if self.nvls is not None:
             self.nvls.zero_grad()
             out = self.model(x, None)
@@ -224,20 +286,18 @@ def sharded_scores(pred_local, gt_local, group=None, want_scores=True, score_fn=
     cols = [shard_bounds(N, q, world) for q in range(world)]
     n_lo, n_hi = cols[rank]
     n_me = n_hi - n_lo
-    # send to rank q: (pred, gt)[my ticks, q's sensors]; receive from rank q: (pred, gt)[q's ticks, my sensors]
-    both = torch.stack([pred_local, gt_local])                                  # [2, T_r, N]
-    send = torch.cat([both[:, :, a:b].reshape(-1) for a, b in cols])
-    in_split = [2 * T_r * (b - a) for a, b in cols]
-    out_split = [2 * tq * n_me for tq in t_counts]
-    recv = torch.empty(sum(out_split), dtype=both.dtype, device=dev)
-    dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split, group=group)
-    parts, off = [], 0
-    for tq, nb in zip(t_counts, out_split):
-        parts.append(recv[off:off + nb].view(2, tq, n_me))
-        off += nb
-    mine = torch.cat(parts, dim=1)                                              # [2, T, n_me]
+    # send to rank q: x[my ticks, q's sensors]; receive from rank q: x[q's ticks, my sensors].  One exchange per
+    # tensor: the receive buffer, filled in rank (= tick) order, IS the contiguous [T, n_me] the scorer reads
+    in_split = [T_r * (b - a) for a, b in cols]
+    out_split = [tq * n_me for tq in t_counts]
+    mine = []
+    for x in (pred_local, gt_local):
+        send = torch.cat([x[:, a:b].reshape(-1) for a, b in cols])
+        recv = torch.empty(T * n_me, dtype=x.dtype, device=dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split, group=group)
+        mine.append(recv.view(T, n_me))
     if n_me > 0:
-        s, top1 = score_fn(mine[0].contiguous(), mine[1].contiguous())
+        s, top1 = score_fn(mine[0], mine[1])
     else:
         s = torch.empty((0, T), dtype=torch.float64, device=dev)
         top1 = torch.full((T,), float("-inf"), dtype=torch.float64, device=dev)

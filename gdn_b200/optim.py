@@ -19,7 +19,9 @@ class FlatAdam:
         if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in self.params):
             raise RuntimeError("FlatAdam needs float32 parameters on one CUDA device (gdn_b200 has no CPU path)")
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
-        self.step_count = 0
+        # the step count lives on the device: `step()` bumps it on the stream and the kernel derives the bias
+        # corrections from it, so the same optimiser works eagerly and inside a captured CUDA graph
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         n = sum(p.numel() for p in self.params)
         self.flat = torch.empty(n, dtype=torch.float32, device=dev)
         self.grad_buffer = torch.zeros(n, dtype=torch.float32, device=dev)      # what the all-reduce works on
@@ -44,12 +46,22 @@ class FlatAdam:
                 p.grad = self.grad_buffer[off:off + k].view_as(p)
             off += k
 
+    @property
+    def step_count(self):
+        """Number of steps taken (reads the device counter: a host sync; graph replays count too)."""
+        return int(self.step_dev.item())
+
+    @step_count.setter
+    def step_count(self, value):
+        self.step_dev.fill_(int(value))
+
     def step(self, grad_scale=1.0):
         lib = _lib.load()
-        self.step_count += 1
-        check(lib.gdn_adam_flat(ptr(self.flat), ptr(self.grad_buffer), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                self.step_count, float(grad_scale), torch.cuda.current_stream().cuda_stream), "gdn_adam_flat")
+        self.step_dev.add_(1)
+        check(lib.gdn_adam_flat_dev(ptr(self.flat), ptr(self.grad_buffer), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                    self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                    ptr(self.step_dev), float(grad_scale), torch.cuda.current_stream().cuda_stream),
+              "gdn_adam_flat_dev")
 
 
 class NvlsFlatAdam:

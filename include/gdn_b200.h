@@ -220,6 +220,11 @@ int    gdn_score(const float* pred, const float* gt, int T, int N, double* score
 int    gdn_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                      float beta1, float beta2, float eps, float weight_decay, long long step, float grad_scale,
                      void* stream);
+/* Same, with the step count read from DEVICE memory when the kernel runs (*step_dev >= 1; the caller increments it
+ * on the same stream before the call): a captured CUDA graph advances Adam's bias correction on every replay. */
+int    gdn_adam_flat_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, const long long* step_dev,
+                         float grad_scale, void* stream);
 /* Data-parallel step over NVSwitch multicast memory (train.py:73 on G ranks): all-reduce of the flat gradient,
  * Adam and the broadcast of the new parameters in one kernel.  params_mc / grads_mc are the MULTICAST addresses of
  * the symmetric flat parameter / gradient buffers (every rank's replica bound to one multicast object, e.g. through

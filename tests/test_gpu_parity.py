@@ -610,3 +610,62 @@ def test_prefetcher_with_a_consumer_that_never_syncs():
     for (sx, sy), (hx, hy) in zip(sums, batches):
         assert abs(sx.item() - hx.float().double().sum().item()) < 1e-6 * hx.numel()
         assert abs(sy.item() - hy.double().sum().item()) < 1e-6 * hy.numel()
+
+
+def test_trainer_replays_fixed_shapes_from_a_cuda_graph():
+    """WindowShardedTrainer (the mirror of train.py:68-73): after two eager steps on a batch shape the step is captured
+    and replayed; a short last batch runs eagerly on the same optimiser state; losses and weights follow the
+    never-graphed trainer."""
+    from gdn_b200.dp import WindowShardedTrainer
+    from gdn_b200.models.GDN import GDN
+    N, W, D, K, B = 51, 5, 64, 15, 32
+    g = torch.Generator(device="cuda").manual_seed(4)
+    xs = [torch.rand(B, N, W, device="cuda", generator=g) for _ in range(6)] + [torch.rand(7, N, W, device="cuda", generator=g)]
+    ys = [torch.rand(x.shape[0], N, device="cuda", generator=g) for x in xs]
+    xs, ys = xs + xs[:2], ys + ys[:2]
+
+    def run(graph):
+        torch.manual_seed(3)
+        m = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()
+        m.dp.p = 0.0
+        tr = WindowShardedTrainer(m, lr=1e-3, cuda_graph=graph)
+        return [tr.step(x, y).item() for x, y in zip(xs, ys)], m, tr
+
+    la, ma, ta = run(False)
+    lb, mb, tb = run(True)
+    assert len(tb._graphs) == 1 and not ta._graphs                       # one shape captured, the 7-window batch eager
+    assert tb.flat.step_count == len(xs) == ta.flat.step_count
+    assert all(abs(p - q) <= 2e-4 * abs(p) for p, q in zip(la, lb)), (la, lb)
+    for (k, p), (_, q) in zip(ma.state_dict().items(), mb.state_dict().items()):
+        if k.endswith("gnn.bias"):
+            continue
+        assert normwise(q.float().cpu(), p.float().cpu()) < (5e-2 if "running_mean" in k else 2e-3), k
+    # dropout on: replays draw fresh masks
+    torch.manual_seed(3)
+    m = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()
+    tr = WindowShardedTrainer(m, lr=0.0, cuda_graph=True)
+    vals = [tr.step(xs[0], ys[0]).item() for _ in range(6)]
+    assert tr._graphs and len(set(vals[2:])) > 1
+
+
+def test_idx_is_rebuilt_from_the_neighbour_table():
+    from gdn_b200 import ops
+    torch.manual_seed(9)
+    for N, D, K, eng in ((300, 64, 9, 0), (2048, 128, 33, 1)):
+        V = (torch.rand(N, D, device="cuda") * 2 - 1) / D ** 0.5
+        V[7] = V[3]                                    # a duplicate: row 7 may rank sensor 3 ahead of itself
+        idx, nbr = ops.graph_build(V, K, use_tensor_cores=eng)
+        assert torch.equal(ops.idx_from_nbr(nbr), idx)
+
+
+def test_loss_reader_returns_every_loss_in_order():
+    from gdn_b200.data import LossReader
+    r = LossReader("cuda")
+    vals = [torch.tensor(float(i) * 0.5, device="cuda") for i in range(7)]
+    got = []
+    for v in vals:
+        out = r.push(v)
+        if out is not None:
+            got.append(out)
+    got += r.flush()
+    assert got == [i * 0.5 for i in range(7)]
