@@ -582,7 +582,11 @@ def run_ours(args):
                              "shuffled window batches gathered by gdn_window_batch (datasets/TimeDataset.py:33-62, train.py:66)"}
         del ds, series
 
-    # ---- per-kernel breakdown of the train step (separate, profiled steps)
+    # ---- per-kernel breakdown of the train step (separate, profiled steps; eager: a graph replay hides the launches
+    # from the event hook -- its kernel count was taken when the graph was captured)
+    graphed = bool(trainer._graphs)
+    graph_launches = max(trainer.graph_launches.values()) if graphed else None
+    trainer.cuda_graph, was_graph = False, trainer.cuda_graph
     lib.gdn_profile_enable(1)
     PSTEPS = 3
     for i in range(PSTEPS):
@@ -590,7 +594,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches, rows = profile_collect(lib)
     lib.gdn_profile_enable(0)
-    per_step_launches = launches // PSTEPS
+    trainer.cuda_graph = was_graph
+    per_step_launches = graph_launches if graphed else launches // PSTEPS
     kernels = {nm: {"launches_per_step": c / PSTEPS, "ms_per_step": t / PSTEPS} for nm, (c, t) in rows.items()}
 
     line = {
@@ -600,6 +605,8 @@ def run_ours(args):
         "config": config_dict(name, wl, world),
         "e2e": e2e, "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,
+        "step_mode": "one CUDA graph per batch shape, replayed (WindowShardedTrainer, captured after two eager steps)" if graphed
+                     else "eager launches",
     }
     if dp_info is not None:
         line["dp_check"] = dp_info

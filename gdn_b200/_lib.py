@@ -44,6 +44,7 @@ _P = C.POINTER
 SIGNATURES = {
     "gdn_version": (C.c_int, []),
     "gdn_last_error": (C.c_char_p, []),
+    "gdn_launch_count": (C.c_longlong, []),
     "gdn_profile_enable": (C.c_int, [C.c_int]),
     "gdn_profile_collect": (C.c_int, [C.c_char_p, C.c_size_t]),
     "gdn_graph_build_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -44,6 +44,9 @@ static void prof_push(const char* name) {
     ++g_prof_n;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 void prof_enter(cudaStream_t st, const char* api) {
     g_prof_stream = st;
     if (g_prof_on) prof_push(api);      // names starting with '@' are API-entry markers
@@ -216,6 +219,8 @@ extern "C" {
 
 int gdn_version(void) { return GDN_B200_VERSION; }
 const char* gdn_last_error(void) { return g_err; }
+
+long long gdn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------- profiler
 int gdn_profile_enable(int on) {

@@ -27,10 +27,12 @@ int  cuda_fail(cudaError_t e, const char* what);
     do {                                                         \
         cudaError_t e__ = cudaGetLastError();                    \
         if (e__ != cudaSuccess) return gdn::cuda_fail(e__, what); \
+        gdn::count_launch();                                     \
         gdn::prof_mark(what);                                    \
     } while (0)
 
 // optional per-kernel timing (gdn_profile_enable): an event is recorded after every launch
+void count_launch();     // every kernel launch the library enqueues (also those recorded into a stream capture)
 void prof_enter(cudaStream_t st, const char* api);
 void prof_mark(const char* what);
 

@@ -126,7 +126,7 @@ class WindowShardedTrainer:
         if cuda_graph is None:
             cuda_graph = os.environ.get("GDN_CUDA_GRAPH", "1") != "0"
         self.cuda_graph = bool(cuda_graph) and self.flat is not None and self.nvls is None and world == 1
-        self._graphs, self._seen, self._drop_counter = {}, {}, None
+        self._graphs, self._seen, self._drop_counter, self.graph_launches = {}, {}, None, {}
         # the graph depends on the (replicated) embedding only: every rank builds 1/world of its rows and the
         # neighbour tables are all-gathered (the one exchange step of the forward; off for a single process)
         if shard_graph is None:
@@ -154,6 +154,8 @@ class WindowShardedTrainer:
         was_training = self.model.training
         self.model.train()
         ops.set_dropout_counter(self._drop_counter)          # the Philox offset is read from a counter the graph bumps
+        from . import _lib
+        n0 = _lib.load().gdn_launch_count()
         try:
             with torch.cuda.graph(graph):
                 self._drop_counter.add_(1)
@@ -162,6 +164,7 @@ class WindowShardedTrainer:
             ops.set_dropout_counter(None)
             self.model.train(was_training)
         self._graphs[key] = (graph, xs, ys, loss)
+        self.graph_launches[key] = int(_lib.load().gdn_launch_count() - n0)    # our kernels per replay
 
     def _graph_step(self, x, y):
         key = (tuple(x.shape), tuple(y.shape), x.dtype, y.dtype, str(x.device))

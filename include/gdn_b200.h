@@ -121,6 +121,9 @@ const char* gdn_last_error(void);
 /* ---- measurement hook (bench.py): when enabled, a CUDA event is recorded on the call's
  * stream after every kernel launch; gdn_profile_collect() synchronises and writes one text
  * line per kernel "<name> <launches> <total_ms>" and returns the number of launches. */
+/* Number of kernel launches the library has enqueued so far in this process (launches recorded into a stream
+ * capture count once, at capture time). */
+long long gdn_launch_count(void);
 int gdn_profile_enable(int on);
 int gdn_profile_collect(char* buf, size_t buf_bytes);
 
