@@ -345,6 +345,36 @@ def dp_gradient_check(dev, rank, world):
         dist.broadcast(ref0, 0)
         out["nvls_replicas_bit_identical"] = bool(torch.equal(mine, ref0))
         out["nvls_pass"] = traj_ok and d2 < 2e-6 and out["nvls_replicas_bit_identical"]
+    # SyncBN: statistics over the global batch -> averaged gradients == the float64 oracle on the CONCATENATED batch
+    def gather(t):
+        parts = [torch.empty_like(t, device=dev) for _ in range(world)]
+        dist.all_gather(parts, t.to(dev))
+        return torch.cat([q.cpu() for q in parts])
+    xg, yg, mg = gather(x), gather(y), gather(mask)
+    m3 = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K)
+    m3.load_state_dict(sd)
+    m3 = m3.to(dev).train()
+    m3.set_dropout_mask(mask.to(dev))
+    tr3 = WindowShardedTrainer(m3, lr=1e-3, flat_adam=True, nvls=False, sync_bn=True, cuda_graph=False)
+    tr3.flat.zero_grad()
+    pred3 = m3(x.to(dev), None)
+    torch.nn.functional.mse_loss(pred3, y.to(dev)).backward()
+    gsum = tr3.flat.grad_buffer.detach().clone()
+    dist.all_reduce(gsum)
+    _, p64g, g64g, _ = go.loss_and_grads(go.cast_state(sd, torch.float64), xg.double(), yg.double(), K, drop_mask=mg.double())
+    refg = torch.cat([g64g[k].reshape(-1) for k in names]).to(dev)
+    errg, off = 0.0, 0
+    for k, p in m3.named_parameters():
+        n = p.numel()
+        if not k.endswith("gnn.bias"):
+            a, b = gsum[off:off + n].double() / world, refg[off:off + n]
+            errg = max(errg, float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)))
+        off += n
+    mine = p64g[rank * Bc:(rank + 1) * Bc].to(dev)
+    perr = float((pred3.detach().double() - mine).abs().max() / mine.abs().max())
+    out["syncbn_grad_max_normwise_err_vs_global_batch_oracle_f64"] = errg
+    out["syncbn_pred_normwise_err_vs_global_batch_oracle_f64"] = perr
+    out["syncbn_pass"] = errg < 1e-4 and perr < 1e-4
     flag = torch.tensor([1.0 if all(v for k, v in out.items() if k.endswith("pass")) else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     out["pass_all_ranks"] = bool(flag.item() > 0)

@@ -39,6 +39,13 @@ class Dropout(C.Structure):
                 ("offset_dev", c_fp)]
 
 
+SYNC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p)
+
+
+class Sync(C.Structure):
+    _fields_ = [("world", C.c_int), ("allreduce_sum_f64", SYNC_FN), ("user", C.c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol include/gdn_b200.h declares
 _P = C.POINTER
 SIGNATURES = {
@@ -67,6 +74,10 @@ SIGNATURES = {
                                 c_fp, c_fp, c_fp, C.c_size_t, c_fp]),
     "gdn_fused_bwd": (C.c_int, [_P(Dims), c_fp, c_fp, c_fp, _P(LayerParams), _P(HeadParams), _P(Dropout), c_fp,
                                 _P(LayerGrads), _P(HeadGrads), c_fp, C.c_size_t, c_fp]),
+    "gdn_fused_fwd_sync": (C.c_int, [_P(Dims), c_fp, c_fp, c_fp, _P(LayerParams), _P(HeadParams), _P(Dropout), C.c_int,
+                                     c_fp, c_fp, c_fp, C.c_size_t, _P(Sync), c_fp]),
+    "gdn_fused_bwd_sync": (C.c_int, [_P(Dims), c_fp, c_fp, c_fp, _P(LayerParams), _P(HeadParams), _P(Dropout), c_fp,
+                                     _P(LayerGrads), _P(HeadGrads), c_fp, C.c_size_t, _P(Sync), c_fp]),
     "gdn_ctx_alpha": (C.c_int, [_P(Dims), c_fp, c_fp, c_fp, c_fp]),
     "gdn_score_ws_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "gdn_score": (C.c_int, [c_fp, c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, C.c_size_t, c_fp]),

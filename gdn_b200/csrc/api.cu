@@ -97,6 +97,8 @@ int num_sms() {
     return v;
 }
 
+size_t sums_stride() { return GDN_SUMS_MAX_DOUBLES; }
+
 int make_shape(const gdn_dims* d, Shape* s, bool need_dwide) {
     GDN_CHECK_ARG(d != nullptr, "dims is NULL");
     GDN_CHECK_ARG(d->B >= 1 && d->N >= 1, "B=%d N=%d must be positive", d->B, d->N);
@@ -169,7 +171,8 @@ WsLayout ws_layout(const Shape& s, bool fused) {
     L.gV = take(&off, (fused && s.S > 1) ? (size_t)s.S * s.N * s.D * sizeof(float) : 0);
     // small: c2[2D] c1[2D] part_u[sms*64] part_e[sms*2D]   (floats)
     L.small = take(&off, ((size_t)4 * s.D + (size_t)num_sms() * (64 + 2 * s.D)) * sizeof(float));
-    L.sums = take(&off, (rec + 64) * sizeof(double));
+    L.sums = take(&off, (size_t)2 * GDN_SUMS_MAX_DOUBLES * sizeof(double));   // local record | rank-summed copy (SyncBN)
+    (void)rec;
     L.total = off;
     return L;
 }
@@ -366,6 +369,12 @@ size_t gdn_fused_ws_bytes(const gdn_dims* d) {
 int gdn_fused_fwd(const gdn_dims* d, const float* x, const float* V, const int32_t* nbr, const gdn_layer_params* p,
                   const gdn_head_params* h, const gdn_dropout* dp, int training, float* pred, void* ctx_, void* ws_,
                   size_t ws_bytes, void* stream) {
+    return gdn_fused_fwd_sync(d, x, V, nbr, p, h, dp, training, pred, ctx_, ws_, ws_bytes, nullptr, stream);
+}
+
+int gdn_fused_fwd_sync(const gdn_dims* d, const float* x, const float* V, const int32_t* nbr, const gdn_layer_params* p,
+                       const gdn_head_params* h, const gdn_dropout* dp, int training, float* pred, void* ctx_, void* ws_,
+                       size_t ws_bytes, const gdn_sync* sync, void* stream) {
     Shape s;
     if (int rc = make_shape(d, &s, true)) return rc;
     GDN_CHECK_ARG(x && V && nbr && p && h && pred && ctx_ && ws_, "fused_fwd: NULL argument");
@@ -388,8 +397,8 @@ int gdn_fused_fwd(const gdn_dims* d, const float* x, const float* V, const int32
         int nrec = 0;
         if (int rc = launch_moments(s, ha.A, part, &nrec, st)) return rc;
         double* sums = (double*)(ws + WL.sums);
-        if (int rc = launch_fin_bn1(s, part, nrec, sums, p, bnc, &h->bn1, st)) return rc;
-        if (int rc = launch_fwd_stats2(s, ha, part, sums, &h->bn2, bnc, st)) return rc;
+        if (int rc = launch_fin_bn1(s, part, nrec, sums, p, bnc, &h->bn1, sync, st)) return rc;
+        if (int rc = launch_fwd_stats2(s, ha, part, sums, &h->bn2, bnc, sync, st)) return rc;
     } else {
         if (int rc = launch_fin_bn_eval(s, p, h, bnc, st)) return rc;
     }
@@ -399,6 +408,13 @@ int gdn_fused_fwd(const gdn_dims* d, const float* x, const float* V, const int32
 int gdn_fused_bwd(const gdn_dims* d, const float* g_pred, const float* V, const int32_t* nbr,
                   const gdn_layer_params* p, const gdn_head_params* h, const gdn_dropout* dp, const void* ctx_,
                   gdn_layer_grads* g, gdn_head_grads* gh, void* ws_, size_t ws_bytes, void* stream) {
+    return gdn_fused_bwd_sync(d, g_pred, V, nbr, p, h, dp, ctx_, g, gh, ws_, ws_bytes, nullptr, stream);
+}
+
+int gdn_fused_bwd_sync(const gdn_dims* d, const float* g_pred, const float* V, const int32_t* nbr,
+                       const gdn_layer_params* p, const gdn_head_params* h, const gdn_dropout* dp, const void* ctx_,
+                       gdn_layer_grads* g, gdn_head_grads* gh, void* ws_, size_t ws_bytes, const gdn_sync* sync,
+                       void* stream) {
     Shape s;
     if (int rc = make_shape(d, &s, true)) return rc;
     GDN_CHECK_ARG(g_pred && V && nbr && p && h && ctx_ && g && gh && ws_, "fused_bwd: NULL argument");
@@ -424,8 +440,8 @@ int gdn_fused_bwd(const gdn_dims* d, const float* g_pred, const float* V, const 
     int nrec = 0;
     prof_enter(st, "@fused_bwd");
     double* sums = (double*)(ws + WL.sums);
-    if (int rc = launch_bwd1(s, ha, ba, part, sums, gh, sm.c2, st)) return rc;
-    if (int rc = launch_bwd2(s, ha, ba, part, sums, gh, sm.c1, g->embedding, st)) return rc;
+    if (int rc = launch_bwd1(s, ha, ba, part, sums, gh, sm.c2, sync, st)) return rc;
+    if (int rc = launch_bwd2(s, ha, ba, part, sums, gh, sm.c1, g->embedding, sync, st)) return rc;
     if (int rc = launch_bwd3(s, ha, ba, part, &nrec, st)) return rc;
     float* gsiT = (float*)(ws + WL.gsiT);
     float* gsjT = (float*)(ws + WL.gsjT);

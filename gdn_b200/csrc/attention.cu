@@ -10,10 +10,10 @@
 //     D-wide transform Wl.A commutes with the aggregation and runs afterwards).
 //
 // Layout: the graph is identical for every window, so a warp owns one target sensor i and
-// 32 windows (lane <-> b).  x is first transposed to xT[N][Bs/32][WP][32] (window index fastest):
-// every gather of a neighbour is then one fully used 128-byte line per (source, w), the
-// neighbour index is warp-uniform, and the backward's scatter into g_sj is one coalesced
-// RED per edge instead of 32 scattered atomics.
+// 32 windows (lane <-> b).  x is first transposed to xT[N][Bs/32][WP/4][32][4] (window index next to
+// fastest, four taps of a window in one 16-byte word): every gather of a neighbour is WP/4 LDG.128 whose
+// 32 lanes cover 512 contiguous bytes, the neighbour index is warp-uniform, and the backward's scatter
+// into g_sj is one coalesced RED per edge instead of 32 scattered atomics.
 #include <stdlib.h>
 #include "common.cuh"
 #include "launchers.h"
@@ -84,31 +84,35 @@ k_prep(const float* __restrict__ x, const float* __restrict__ V, const float* __
         float si = 0.f, sj = 0.f;
         const bool ok = b < B;
         const float* row = x + ((size_t)b * N + i) * W;
-        float* dst = xT + ((size_t)i * chunks + c) * WP * 32 + lane;
+        // xT quad layout: [N][C][WP/4][32 lanes][4 taps] -- a lane's four consecutive taps are one 16-byte word
+        float* dst = xT + ((size_t)i * chunks + c) * WP * 32 + lane * 4;
         if (vec4) {
-            // 16-byte loads (W % 4 == 0 and x 16-byte aligned): a lane's row is W contiguous floats, rows of different lanes are N*W apart, so the
-            // number of L1 requests (each touching 32 lines) is what bounds this kernel
+            // 16-byte loads (W % 4 == 0 and x 16-byte aligned): a lane's row is W contiguous floats, rows of different
+            // lanes are N*W apart; 16-byte stores land as full 512-byte runs per warp
             for (int w = 0; w < WP; w += 4) {
                 float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (ok && w < W) q = __ldg(reinterpret_cast<const float4*>(row + w));
+                *reinterpret_cast<float4*>(dst + (w >> 2) * 128) = q;
                 const float v4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (w + u < W) {
+                        si = fmaf(v4[u], uv[w + u], si);
+                        sj = fmaf(v4[u], uv[32 + w + u], sj);
+                    }
+            }
+        } else {
+            for (int w = 0; w < WP; w += 4) {
+                float v4[4];
+#pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    dst[(w + u) * 32] = v4[u];
+                    v4[u] = (ok && w + u < W) ? __ldg(row + w + u) : 0.f;
                     if (w + u < W) {
                         si = fmaf(v4[u], uv[w + u], si);
                         sj = fmaf(v4[u], uv[32 + w + u], sj);
                     }
                 }
-            }
-        } else {
-            for (int w = 0; w < WP; ++w) {
-                const float v = (ok && w < W) ? __ldg(row + w) : 0.f;
-                dst[w * 32] = v;
-                if (w < W) {
-                    si = fmaf(v, uv[w], si);
-                    sj = fmaf(v, uv[32 + w], sj);
-                }
+                *reinterpret_cast<float4*>(dst + (w >> 2) * 128) = make_float4(v4[0], v4[1], v4[2], v4[3]);
             }
         }
         siT[(size_t)i * Bs + b] = ok ? si + ei : 0.f;
@@ -161,7 +165,7 @@ k_attn_fwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
         const int b = c * 32 + lane;
         const int32_t* nb = nbr + (size_t)i * Kp;
         const float* sjb = sjT + b;
-        const float* xb = xT + (size_t)c * WP * 32 + lane;
+        const float4* xb = reinterpret_cast<const float4*>(xT + (size_t)c * WP * 32) + lane;
         const float si = siT[(size_t)i * Bs + b];
         float m = -INFINITY;
         int deg = 0;
@@ -180,9 +184,15 @@ k_attn_fwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
             const unsigned src = (unsigned)__ldg(nb + k);
             const float p = expf(leaky(si + sjb[src * (unsigned)Bs]) - m);
             sum += p;
-            const float* xs = xb + src * xstride;
+            const float4* xs = xb + src * (xstride >> 2);
 #pragma unroll
-            for (int w = 0; w < WP; ++w) acc[w] = fmaf(p, xs[w * 32], acc[w]);
+            for (int q = 0; q < WP / 4; ++q) {
+                const float4 v = xs[q * 32];
+                acc[4 * q] = fmaf(p, v.x, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(p, v.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(p, v.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(p, v.w, acc[4 * q + 3]);
+            }
         }
         const float linv = 1.f / (sum + GDN_SOFTMAX_EPS);
         mT[(size_t)i * Bs + b] = m;
@@ -303,7 +313,7 @@ k_attn_bwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
         const int32_t* nb = nbr + (size_t)i * Kp;
         const float* sjb = sjT + b;
         float* gsjb = gsjT + b;
-        const float* xb = xT + (size_t)c * WP * 32 + lane;
+        const float4* xb = reinterpret_cast<const float4*>(xT + (size_t)c * WP * 32) + lane;
         const float si = siT[(size_t)i * Bs + b];
         const float m = mT[(size_t)i * Bs + b], linv = linvT[(size_t)i * Bs + b];
         float g[WP];
@@ -325,12 +335,15 @@ k_attn_bwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
             const unsigned src = (unsigned)__ldg(nb + k);
             const float pre = si + sjb[src * (unsigned)Bs];
             const float a = expf(leaky(pre) - m) * linv;
-            const float* xs = xb + src * xstride;
+            const float4* xs = xb + src * (xstride >> 2);
             float ga0 = 0.f, ga1 = 0.f;
 #pragma unroll
-            for (int w = 0; w < WP; w += 2) {
-                ga0 = fmaf(g[w], xs[w * 32], ga0);
-                ga1 = fmaf(g[w + 1], xs[(w + 1) * 32], ga1);
+            for (int q = 0; q < WP / 4; ++q) {                 // same summation order as before: even taps, odd taps
+                const float4 v = xs[q * 32];
+                ga0 = fmaf(g[4 * q], v.x, ga0);
+                ga1 = fmaf(g[4 * q + 1], v.y, ga1);
+                ga0 = fmaf(g[4 * q + 2], v.z, ga0);
+                ga1 = fmaf(g[4 * q + 3], v.w, ga1);
             }
             const float gl = a * ((ga0 + ga1) - dot);
             const float gp = pre > 0.f ? gl : GDN_NEG_SLOPE * gl;
@@ -398,12 +411,16 @@ k_attn_tail(const float* __restrict__ xT, const float* __restrict__ gsiT, const 
             const float gi = gsiT[(size_t)i * Bs + b], gj = gsjT[(size_t)i * Bs + b];
             ssi += gi;
             ssj += gj;
-            const float* xs = xT + ((size_t)i * chunks + c) * WP * 32 + lane;
+            const float4* xs = reinterpret_cast<const float4*>(xT + ((size_t)i * chunks + c) * WP * 32) + lane;
 #pragma unroll
-            for (int w = 0; w < WP; ++w) {
-                const float xv = xs[w * 32];
-                aui[w] = fmaf(gi, xv, aui[w]);
-                auj[w] = fmaf(gj, xv, auj[w]);
+            for (int q = 0; q < WP / 4; ++q) {
+                const float4 v = xs[q * 32];
+                const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    aui[4 * q + u] = fmaf(gi, xv[u], aui[4 * q + u]);
+                    auj[4 * q + u] = fmaf(gj, xv[u], auj[4 * q + u]);
+                }
             }
         }
         ssi = warp_sum(ssi);

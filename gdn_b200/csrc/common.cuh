@@ -65,7 +65,7 @@ struct Shape {
 int make_shape(const gdn_dims* d, Shape* s, bool need_dwide);
 
 struct CtxLayout {
-    size_t xT;      // [N][Bs/32][WP][32]  x transposed: window index fastest, w zero-padded to WP
+    size_t xT;      // [N][Bs/32][WP/4][32][4]  x transposed: (window, tap quad) fastest, w zero-padded to WP
     size_t siT;     // [N][Bs]      s_i = x.u_i + e_i
     size_t sjT;     // [N][Bs]      s_j = x.u_j + e_j
     size_t mT;      // [N][Bs]      segment max of the leaky-relu'd logits
@@ -95,6 +95,8 @@ struct WsLayout {
 };
 WsLayout ws_layout(const Shape& s, bool fused);
 
+size_t sums_stride();             // doubles between the local and the rank-summed copy inside WsLayout::sums (SyncBN)
+#define GDN_SUMS_MAX_DOUBLES 8768  // >= max(D*W + D, 3D + 32, W*W + W) + 64 for D <= 256, W <= 32
 #define GDN_MAX_PART_CTAS 1184     // 148 SMs x 8: upper bound on CTAs that write partials
 
 }  // namespace gdn

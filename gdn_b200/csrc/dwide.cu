@@ -1496,7 +1496,8 @@ __global__ void k_fin_bn_eval(int D, const float* __restrict__ bias,
 }
 
 // pass-1 sums -> g_wo, g_gamma2, g_beta2, g_bo and the pass-2 coefficients c2 = (g_beta2/n, g_gamma2/n)
-__global__ void k_fin_bwd1(const double* __restrict__ part, int nrec, long long n, int D,
+// `glob` = the same record summed over the data-parallel ranks (SyncBN), n = rows of ALL ranks; NULL: this rank only
+__global__ void k_fin_bwd1(const double* __restrict__ part, int nrec, const double* __restrict__ glob, long long n, int D,
                            float* __restrict__ g_wo, float* __restrict__ g_g2, float* __restrict__ g_b2,
                            float* __restrict__ g_bo, float* __restrict__ c2) {
     const int rec = 3 * D + 32;
@@ -1506,6 +1507,7 @@ __global__ void k_fin_bwd1(const double* __restrict__ part, int nrec, long long 
             a += part[(size_t)q * rec + d]; b += part[(size_t)q * rec + D + d]; c += part[(size_t)q * rec + 2 * D + d];
         }
         g_wo[d] = (float)a; g_g2[d] = (float)b; g_b2[d] = (float)c;
+        if (glob != nullptr) { b = glob[D + d]; c = glob[2 * D + d]; }
         c2[d] = (float)(c / (double)n);
         c2[D + d] = (float)(b / (double)n);
     }
@@ -1516,12 +1518,13 @@ __global__ void k_fin_bwd1(const double* __restrict__ part, int nrec, long long 
     }
 }
 
-__global__ void k_fin_bwd2(const double* __restrict__ part, int nrec, long long n, int D,
+__global__ void k_fin_bwd2(const double* __restrict__ part, int nrec, const double* __restrict__ glob, long long n, int D,
                            float* __restrict__ g_g1, float* __restrict__ g_b1, float* __restrict__ c1) {
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         double b = 0.0, c = 0.0;
         for (int q = 0; q < nrec; ++q) { b += part[(size_t)q * 2 * D + d]; c += part[(size_t)q * 2 * D + D + d]; }
         g_g1[d] = (float)b; g_b1[d] = (float)c;
+        if (glob != nullptr) { b = glob[d]; c = glob[D + d]; }
         c1[d] = (float)(c / (double)n);
         c1[D + d] = (float)(b / (double)n);
     }
@@ -1672,11 +1675,29 @@ int launch_moments(const Shape& s, const float* A, double* part, int* nrec, cuda
     return 0;
 }
 
+// SyncBN: `count` reduced doubles at `local` -> their sum over the ranks at local + stride (the second half of the
+// `sums` region); returns that pointer, or NULL when statistics are per rank
+static bool sync_on(const gdn_sync* sy) { return sy != nullptr && sy->world > 1 && sy->allreduce_sum_f64 != nullptr; }
+static int sync_sums(const gdn_sync* sy, double* local, int count, double** global_out, cudaStream_t st) {
+    *global_out = nullptr;
+    if (!sync_on(sy)) return 0;
+    double* glob = local + sums_stride();
+    cudaError_t e = cudaMemcpyAsync(glob, local, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "sync_sums copy");
+    const int rc = sy->allreduce_sum_f64(glob, (long long)count, sy->user, (void*)st);
+    if (rc != 0) { set_error("SyncBN all-reduce callback failed (rc=%d)", rc); return rc > 0 ? -2 : rc; }
+    *global_out = glob;
+    return 0;
+}
+static long long rows_total(const Shape& s, const gdn_sync* sy) { return sync_on(sy) ? s.n * (long long)sy->world : s.n; }
+
 int launch_fin_bn1(const Shape& s, const double* part, int nrec, double* sums, const gdn_layer_params* p, float* bnc,
-                   const gdn_bn* bn, cudaStream_t st) {
+                   const gdn_bn* bn, const gdn_sync* sync, cudaStream_t st) {
     const size_t smem = ((size_t)s.W * s.W + s.W) * sizeof(double);
     if (int rc = reduce_part<double>(part, nrec, s.W * s.W + s.W, sums, st)) return rc;
-    k_fin_bn1<<<1, 256, smem, st>>>(sums, 1, s.n, s.W, s.D, p->lin_weight, p->bias, bnc,
+    double* glob = nullptr;
+    if (int rc = sync_sums(sync, sums, s.W * s.W + s.W, &glob, st)) return rc;
+    k_fin_bn1<<<1, 256, smem, st>>>(glob ? glob : sums, 1, rows_total(s, sync), s.W, s.D, p->lin_weight, p->bias, bnc,
                                     bn->running_mean, bn->running_var, (long long*)bn->num_batches_tracked);
     GDN_CHECK_LAUNCH("k_fin_bn1");
     return 0;
@@ -1692,14 +1713,16 @@ int launch_fin_bn_eval(const Shape& s, const gdn_layer_params* p, const gdn_head
 
 
 int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, double* sums, const gdn_bn* bn, float* bnc,
-                      cudaStream_t st) {
+                      const gdn_sync* sync, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
 #define CALL(DPLC, WPC) GDN_LAUNCH_DYN((k_fwd_stats2<DPLC, WPC>), grid, (dw_smem2<DPLC, WPC>(true, false, 2 * DPLC, false)), st, h, part)
     GDN_DISPATCH_DW(s.DPL, s.WP, CALL);
 #undef CALL
     GDN_CHECK_LAUNCH("k_fwd_stats2");
     if (int rc = reduce_part<double>(part, grid, 2 * s.D, sums, st)) return rc;
-    k_fin_bn2<<<1, 256, 0, st>>>(sums, 1, s.n, s.D, bnc, bn->running_mean, bn->running_var,
+    double* glob = nullptr;
+    if (int rc = sync_sums(sync, sums, 2 * s.D, &glob, st)) return rc;
+    k_fin_bn2<<<1, 256, 0, st>>>(glob ? glob : sums, 1, rows_total(s, sync), s.D, bnc, bn->running_mean, bn->running_var,
                                  (long long*)bn->num_batches_tracked);
     GDN_CHECK_LAUNCH("k_fin_bn2");
     return 0;
@@ -1720,7 +1743,7 @@ int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t 
 }
 
 int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
-                float* c2, cudaStream_t st) {
+                float* c2, const gdn_sync* sync, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
     const bool buf = h.xh1 != nullptr;
 #define CALL(DPLC, WPC)                                                                                             \
@@ -1732,13 +1755,15 @@ int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd1");
     if (int rc = reduce_part<double>(part, grid, 3 * s.D + 32, sums, st)) return rc;
-    k_fin_bwd1<<<1, 256, 0, st>>>(sums, 1, s.n, s.D, gh->out_w, gh->bn2_weight, gh->bn2_bias, gh->out_b, c2);
+    double* glob = nullptr;
+    if (int rc = sync_sums(sync, sums, 3 * s.D + 32, &glob, st)) return rc;
+    k_fin_bwd1<<<1, 256, 0, st>>>(sums, 1, glob, rows_total(s, sync), s.D, gh->out_w, gh->bn2_weight, gh->bn2_bias, gh->out_b, c2);
     GDN_CHECK_LAUNCH("k_fin_bwd1");
     return 0;
 }
 
 int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
-                float* c1, float* gV_final, cudaStream_t st) {
+                float* c1, float* gV_final, const gdn_sync* sync, cudaStream_t st) {
     const int grid = dw_grid((long long)s.N * s.S);
     const bool buf = h.xh1 != nullptr;
 #define CALL(DPLC, WPC)                                                                                             \
@@ -1750,7 +1775,9 @@ int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* par
 #undef CALL
     GDN_CHECK_LAUNCH("k_bwd2");
     if (int rc = reduce_part<double>(part, grid, 2 * s.D, sums, st)) return rc;
-    k_fin_bwd2<<<1, 256, 0, st>>>(sums, 1, s.n, s.D, gh->bn1_weight, gh->bn1_bias, c1);
+    double* glob = nullptr;
+    if (int rc = sync_sums(sync, sums, 2 * s.D, &glob, st)) return rc;
+    k_fin_bwd2<<<1, 256, 0, st>>>(sums, 1, glob, rows_total(s, sync), s.D, gh->bn1_weight, gh->bn1_bias, c1);
     GDN_CHECK_LAUNCH("k_fin_bwd2");
     if (s.S > 1) {
         const long long ND = (long long)s.N * s.D;

@@ -49,16 +49,16 @@ int launch_lin_bwd(const Shape& s, const float* gout, const float* A, const gdn_
                    double* part, int* nrec, cudaStream_t st);
 int launch_moments(const Shape& s, const float* A, double* part, int* nrec, cudaStream_t st);
 int launch_fin_bn1(const Shape& s, const double* part, int nrec, double* sums, const gdn_layer_params* p, float* bnc,
-                   const gdn_bn* bn, cudaStream_t st);
+                   const gdn_bn* bn, const gdn_sync* sync, cudaStream_t st);
 int launch_fin_bn_eval(const Shape& s, const gdn_layer_params* p, const gdn_head_params* h, float* bnc,
                        cudaStream_t st);
 int launch_fwd_stats2(const Shape& s, const HeadArgs& h, double* part, double* sums, const gdn_bn* bn, float* bnc,
-                      cudaStream_t st);
+                      const gdn_sync* sync, cudaStream_t st);
 int launch_fwd_out(const Shape& s, const HeadArgs& h, float* pred, cudaStream_t st);
 int launch_bwd1(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
-                float* c2, cudaStream_t st);
+                float* c2, const gdn_sync* sync, cudaStream_t st);
 int launch_bwd2(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, double* sums, gdn_head_grads* gh,
-                float* c1, float* gV_final, cudaStream_t st);
+                float* c1, float* gV_final, const gdn_sync* sync, cudaStream_t st);
 int launch_bwd3(const Shape& s, const HeadArgs& h, const BwdArgs& g, double* part, int* nrec, cudaStream_t st);
 
 // graph_build.cu

@@ -79,7 +79,7 @@ class WindowShardedTrainer:
     GRAPH_MAX_ELEMS = 1 << 21          # batches up to this many input values are replayed from a CUDA graph
 
     def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, shard_graph=None, flat_adam=None,
-                 nvls=None, cuda_graph=None):
+                 nvls=None, cuda_graph=None, sync_bn=False):
         """flat_adam (default on CUDA): parameters, gradients and Adam moments live in flat buffers
         (`gdn_b200.optim.FlatAdam`): autograd accumulates straight into the buffer the all-reduce works on, and the
         1/world scaling is fused into the single Adam kernel -- no `torch.cat`, no `mul_`, no re-pointing of `.grad`
@@ -123,6 +123,9 @@ class WindowShardedTrainer:
                 kw["fused"] = True
             self.opt = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, **kw)
             self.reduce = FlatGradAllReduce(params, group)
+        # sync_bn: BatchNorm statistics over the global batch (GDN.sync_batchnorm) instead of per-rank (DDP) statistics
+        if sync_bn and world > 1 and hasattr(model, "sync_batchnorm"):
+            model.sync_batchnorm(group)
         if cuda_graph is None:
             cuda_graph = os.environ.get("GDN_CUDA_GRAPH", "1") != "0"
         self.cuda_graph = bool(cuda_graph) and self.flat is not None and self.nvls is None and world == 1

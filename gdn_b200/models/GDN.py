@@ -124,6 +124,7 @@ class GDN(nn.Module):
         self._kth = None                  # per-row K-th cosine of the last graph build (warm-start hint)
         self.graph_margin = 0.03          # admission slack below that hint
         self._graph_shard = None          # (rank, world, group): row-sharded graph build + all-gather (data parallel)
+        self._bn_sync = None              # ops.BatchNormSync: BatchNorm statistics over the global batch (data parallel)
 
     def init_params(self):
         nn.init.kaiming_uniform_(self.embedding.weight, a=math.sqrt(5))
@@ -133,6 +134,15 @@ class GDN(nn.Module):
         """Test hook: use this keep mask ([B, N, D], values 0 or 1/(1-p)) instead of Philox for the
         next training forwards (None restores the in-kernel RNG)."""
         self._dropout_mask = mask
+
+    def sync_batchnorm(self, group=None, enable=True):
+        """Data-parallel training with BatchNorm statistics of the GLOBAL batch (torch's SyncBatchNorm semantics for
+        models/GDN.py:77,179): results then equal the reference run on the concatenated batch, not on each rank's
+        shard.  Four all-reduces of a few hundred doubles per step; every rank must feed the same number
+        of windows.  Training forwards only; evaluation uses the running statistics as always."""
+        self._bn_sync = ops.BatchNormSync(group) if enable else None
+        if self._bn_sync is not None and self._bn_sync.world <= 1:
+            self._bn_sync = None
 
     def shard_graph_build(self, rank, world, group=None):
         """Data-parallel training: the embedding is replicated, so the graph is identical on every rank -- build
@@ -211,7 +221,7 @@ class GDN(nn.Module):
             bn1.weight, bn1.bias, bn2.weight, bn2.bias, lin.weight, lin.bias,
             (bn1.running_mean, bn1.running_var, bn1.num_batches_tracked),
             (bn2.running_mean, bn2.running_var, bn2.num_batches_tracked),
-            training, self._dropout_mask if training else None, float(self.dp.p))
+            training, self._dropout_mask if training else None, float(self.dp.p), self._bn_sync if training else None)
         # attention weights / edge list (models/GDN.py:74-75) are rebuilt from the saved state on demand
         layer._att_eager = None
         layer._att_lazy = (blob, nbr, (x.shape[0], x.shape[1], x.shape[2], self.dim, int(self.topk)))

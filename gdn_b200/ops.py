@@ -188,12 +188,49 @@ class _DropState:
         return seed & 0xFFFFFFFFFFFFFFFF, off
 
 
+class BatchNormSync:
+    """SyncBN for the fused path: the library calls back at the four points where a BatchNorm needs
+    batch-wide sums; the callback all-reduces that small buffer of doubles (a slice of the call's workspace blob) over
+    the process group on the current stream.  Rows per rank must be equal."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.ws = None
+        self.error = None
+        self._cb = _lib.SYNC_FN(self._allreduce)           # keep the thunk alive as long as this object
+        self.struct = _lib.Sync(self.world, self._cb, None)
+
+    def _allreduce(self, buf, count, _user, _stream):
+        try:
+            ws = self.ws
+            off = int(buf) - ws.data_ptr()
+            if off < 0 or off + 8 * count > ws.numel() or off % 8:
+                raise RuntimeError("SyncBN buffer lies outside the workspace")
+            self.dist.all_reduce(ws[off:off + 8 * count].view(torch.float64), group=self.group)
+            return 0
+        except BaseException as e:                          # never let an exception cross the C frame
+            self.error = e
+            return 1
+
+    def pointer(self, ws):
+        self.ws, self.error = ws, None
+        return C.byref(self.struct)
+
+    def check(self):
+        self.ws = None
+        if self.error is not None:
+            e, self.error = self.error, None
+            raise e
+
+
 class FusedGDNFn(torch.autograd.Function):
     """Whole GDN forward/backward for out_layer_num == 1 (models/GDN.py:122-187)."""
 
     @staticmethod
     def forward(ctx, x, V, nbr, lin_w, att_i, att_j, att_em_i, att_em_j, bias,
-                bn1_w, bn1_b, bn2_w, bn2_b, out_w, out_b, bn1_buf, bn2_buf, training, drop_mask, drop_p):
+                bn1_w, bn1_b, bn2_w, bn2_b, out_w, out_b, bn1_buf, bn2_buf, training, drop_mask, drop_p, sync=None):
         lib = _lib.load()
         _need_cuda(x, "data")
         xc, Vc = _f32c(x), _f32c(V)
@@ -235,9 +272,14 @@ class FusedGDNFn(torch.autograd.Function):
         blob = _blob(nb_ctx, dev)
         ws = _blob(lib.gdn_fused_ws_bytes(C.byref(dims)), dev)
         pred = torch.empty((B, N), dtype=torch.float32, device=dev)
-        check(lib.gdn_fused_fwd(C.byref(dims), ptr(xc), ptr(Vc), ptr(nbr), C.byref(lp), C.byref(hp), C.byref(dp),
-                                1 if training else 0, ptr(pred), ptr(blob), ptr(ws), ws.numel(), _stream()),
-              "gdn_fused_fwd")
+        use_sync = sync is not None and training and sync.world > 1
+        rc = lib.gdn_fused_fwd_sync(C.byref(dims), ptr(xc), ptr(Vc), ptr(nbr), C.byref(lp), C.byref(hp), C.byref(dp),
+                                    1 if training else 0, ptr(pred), ptr(blob), ptr(ws), ws.numel(),
+                                    sync.pointer(ws) if use_sync else None, _stream())
+        if use_sync:
+            sync.check()
+        check(rc, "gdn_fused_fwd")
+        ctx.sync = sync if use_sync else None
         ctx.dims = (B, N, W, D, K)
         ctx.training = bool(training)
         ctx.drop = (seed, offset, float(drop_p))
@@ -273,10 +315,14 @@ class FusedGDNFn(torch.autograd.Function):
         lg = LayerGrads(*[t.data_ptr() for t in g_layer], g_V.data_ptr())
         hg = HeadGrads(*[t.data_ptr() for t in g_head])
         ws = _blob(lib.gdn_fused_ws_bytes(C.byref(dims)), dev)
-        check(lib.gdn_fused_bwd(C.byref(dims), ptr(g_pred), ptr(Vc), ptr(nbr), C.byref(lp), C.byref(hp),
-                                C.byref(dp), ptr(blob), C.byref(lg), C.byref(hg), ptr(ws), ws.numel(), _stream()),
-              "gdn_fused_bwd")
-        return (None, g_V, None, *g_layer, *g_head, None, None, None, None, None)
+        sync = ctx.sync
+        rc = lib.gdn_fused_bwd_sync(C.byref(dims), ptr(g_pred), ptr(Vc), ptr(nbr), C.byref(lp), C.byref(hp),
+                                    C.byref(dp), ptr(blob), C.byref(lg), C.byref(hg), ptr(ws), ws.numel(),
+                                    sync.pointer(ws) if sync is not None else None, _stream())
+        if sync is not None:
+            sync.check()
+        check(rc, "gdn_fused_bwd")
+        return (None, g_V, None, *g_layer, *g_head, None, None, None, None, None, None)
 
 
 def ctx_alpha(blob, nbr, B, N, W, D, K):

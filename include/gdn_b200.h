@@ -115,6 +115,16 @@ typedef struct gdn_dropout {
                                    captured CUDA graph draw a fresh mask on every replay (may be NULL) */
 } gdn_dropout;
 
+/* Synchronised BatchNorm for data-parallel training (models/GDN.py:77,179 evaluated on the GLOBAL batch instead of
+ * this rank's shard).  The library owns no communicator: at the four points where a BatchNorm
+ * needs batch-wide sums (two in the forward, two in the backward) it calls back with a small buffer of doubles to be
+ * summed over the ranks IN PLACE, ordered on `stream`.  world = number of ranks (rows per rank must be equal). */
+typedef struct gdn_sync {
+    int world;
+    int (*allreduce_sum_f64)(void* buf, long long count, void* user, void* stream);  /* 0 = ok */
+    void* user;
+} gdn_sync;
+
 int         gdn_version(void);
 const char* gdn_last_error(void);
 
@@ -205,6 +215,17 @@ int    gdn_fused_bwd(const gdn_dims* d, const float* g_pred, const float* V, con
                      const gdn_layer_params* p, const gdn_head_params* h, const gdn_dropout* dp,
                      const void* ctx, gdn_layer_grads* g, gdn_head_grads* gh,
                      void* ws, size_t ws_bytes, void* stream);
+/* Same with BatchNorm statistics (forward) and the BatchNorm backward's batch sums shared by `sync->world` ranks;
+ * parameter gradients stay this rank's partial sums (the caller's gradient all-reduce completes them).  sync == NULL
+ * or world <= 1: identical to the calls above. */
+int    gdn_fused_fwd_sync(const gdn_dims* d, const float* x, const float* V, const int32_t* nbr,
+                          const gdn_layer_params* p, const gdn_head_params* h, const gdn_dropout* dp,
+                          int training, float* pred, void* ctx, void* ws, size_t ws_bytes, const gdn_sync* sync,
+                          void* stream);
+int    gdn_fused_bwd_sync(const gdn_dims* d, const float* g_pred, const float* V, const int32_t* nbr,
+                          const gdn_layer_params* p, const gdn_head_params* h, const gdn_dropout* dp,
+                          const void* ctx, gdn_layer_grads* g, gdn_head_grads* gh,
+                          void* ws, size_t ws_bytes, const gdn_sync* sync, void* stream);
 /* attention weights of the last gdn_fused_fwd / gdn_graphlayer_fwd held in ctx:
  * alpha [B*N, K+1] (GNNLayer.att_weight_1, materialised only on demand). */
 int    gdn_ctx_alpha(const gdn_dims* d, const int32_t* nbr, const void* ctx, float* alpha, void* stream);
