@@ -393,7 +393,8 @@ def sharded_score_leg(model, xs, dev, rank, world, B, N, flush, timed_max):
     pl, gl = torch.rand(hi - lo, N, device=dev, generator=g), torch.rand(hi - lo, N, device=dev, generator=g)
     with torch.no_grad():
         ev = timed_max(lambda i: model(xs[i % len(xs)], None), 5, 3)
-        sc = timed_max(lambda i: sharded_scores(pl, gl, want_scores=True), 5, 2)
+        ticks = [shard_bounds(T, q, world)[1] - shard_bounds(T, q, world)[0] for q in range(world)]
+        sc = timed_max(lambda i: sharded_scores(pl, gl, want_scores=True, tick_counts=ticks), 5, 2)
     model.train()
     ev_wps = world * B / (ev * 1e-3)
     sc_tps = T / (sc * 1e-3)

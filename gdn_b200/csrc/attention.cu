@@ -294,8 +294,8 @@ __global__ void k_attn_alpha(const float* __restrict__ siT, const float* __restr
 // dot needs no pass of its own: sum_k alpha_k (g_A . x_k) = g_A . (sum_k alpha_k x_k) = g_A . A, and A
 // is saved by the forward.  One sweep over the edges, no stash, no second exp.
 // ---------------------------------------------------------------------------------------
-template <int WP>
-__global__ void __launch_bounds__(256, 2)
+template <int WP, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_attn_bwd(const float* __restrict__ xT, const float* __restrict__ siT, const float* __restrict__ sjT,
            const float* __restrict__ mT, const float* __restrict__ linvT,
            const int32_t* __restrict__ nbr, const float* __restrict__ gA, const float* __restrict__ A,
@@ -636,11 +636,16 @@ int launch_attn_bwd(const Shape& s, const int32_t* nbr, const char* ctx, const C
     if (e != cudaSuccess) return cuda_fail(e, "memset g_sj");
     const int grid = grid_for_warps(tasks, 8, 32 * num_sms());
     const float* Arows = (const float*)(ctx + L.A);
-#define GDN_LAUNCH_AB(WPV)                                                                              \
-    k_attn_bwd<WPV><<<grid, 256, 0, st>>>(xT, siT, sjT, mT, linvT, nbr, gA, Arows, s.B, s.N, s.W, s.Kp, s.Bs, gsiT, gsjT)
-    if (s.WP == 8) GDN_LAUNCH_AB(8);
-    else if (s.WP == 16) GDN_LAUNCH_AB(16);
-    else GDN_LAUNCH_AB(32);
+#define GDN_LAUNCH_AB(WPV, MINB)                                                                        \
+    k_attn_bwd<WPV, MINB><<<grid, 256, 0, st>>>(xT, siT, sjT, mT, linvT, nbr, gA, Arows, s.B, s.N, s.W, s.Kp, s.Bs, gsiT, gsjT)
+    static int minb = -1;                         // diagnostics: GDN_ATTN_BWD_MINB = 2 | 3 | 4 (slide_win 9..16)
+    if (minb < 0) { const char* e = getenv("GDN_ATTN_BWD_MINB"); minb = e ? atoi(e) : 3; }
+    if (s.WP == 8) GDN_LAUNCH_AB(8, 4);
+    else if (s.WP == 16) {
+        if (minb == 2) GDN_LAUNCH_AB(16, 2);
+        else if (minb == 4) GDN_LAUNCH_AB(16, 4);
+        else GDN_LAUNCH_AB(16, 3);
+    } else GDN_LAUNCH_AB(32, 2);
 #undef GDN_LAUNCH_AB
     GDN_CHECK_LAUNCH("k_attn_bwd");
     return 0;

@@ -267,13 +267,15 @@ def sharded_test(model, dataloader, group=None):
     return float(acc[0].item() / max(acc[1].item(), 1.0)), pred, gt, lab[:, 0] if lab.dim() == 2 else lab
 
 
-def sharded_scores(pred_local, gt_local, group=None, want_scores=True, score_fn=None):
+def sharded_scores(pred_local, gt_local, group=None, want_scores=True, score_fn=None, tick_counts=None):
     """evaluate.py:6-36 + 134-139 on `world` ranks ("Scoring shards by sensor ... final gather of [T]
     maxima").  Input: this rank's contiguous tick range [T_r, N] of predictions / ground truth (ranks in tick order,
     as `sharded_test` leaves them).  The scorer needs whole series per sensor, so the one exchange step is an
     all-to-all that turns the tick sharding into a sensor sharding ([T_r, N] -> [T, N_r], 8 T N / world bytes per
     rank); every rank then scores its N_r sensors, and the per-tick maximum over sensors is one all-reduce(MAX) of
-    [T] doubles.  Returns (scores_local [N_r, T] float64 or None, top1 [T] float64 on every rank, (n_lo, n_hi))."""
+    [T] doubles.  `tick_counts` (ticks held by every rank, in rank order) saves the size exchange and its host sync
+    when the caller knows them (sharded_test's contiguous split does).
+    Returns (scores_local [N_r, T] float64 or None, top1 [T] float64 on every rank, (n_lo, n_hi))."""
     from . import ops
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
@@ -284,10 +286,15 @@ def sharded_scores(pred_local, gt_local, group=None, want_scores=True, score_fn=
     if world == 1:
         s, top1 = score_fn(pred_local.contiguous(), gt_local.contiguous())
         return s, top1, (0, N)
-    counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    counts[rank] = T_r
-    dist.all_reduce(counts, group=group)
-    t_counts = [int(c) for c in counts.tolist()]
+    if tick_counts is not None:
+        t_counts = [int(c) for c in tick_counts]
+        if len(t_counts) != world or t_counts[rank] != T_r:
+            raise ValueError("tick_counts must list every rank's tick count (this rank's included)")
+    else:
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        counts[rank] = T_r
+        dist.all_reduce(counts, group=group)
+        t_counts = [int(c) for c in counts.tolist()]
     T = sum(t_counts)
     cols = [shard_bounds(N, q, world) for q in range(world)]
     n_lo, n_hi = cols[rank]

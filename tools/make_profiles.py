@@ -1,7 +1,8 @@
-"""Build profiles/r01_* from the CSVs tools/gpu_profiles_final.sh brought back in gpurun_out/:
+"""Build profiles/rNN_* (python tools/make_profiles.py r02) from the CSVs tools/gpu_profiles_final.sh brought back in gpurun_out/:
    r01_traffic.json (DRAM bytes of one GraphLayer fwd+bwd, per kernel, from ncu --set full),
    r01_ncu_C5.md    (launch-list shares of the bench command next to bench.py's live breakdown; full-set tables)."""
 import collections, csv, io, json, os, re, shutil, subprocess, sys
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC, DST = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 num = lambda v: float(v.replace(",", "") or 0)
@@ -15,7 +16,7 @@ def raw_rows(path):
 
 traffic = {}
 for w in ("C4", "C5"):
-    hdr, units, data = raw_rows(os.path.join(SRC, f"r01_ncu_{w}_graphlayer_raw.csv"))
+    hdr, units, data = raw_rows(os.path.join(SRC, f"{R}_ncu_{w}_graphlayer_raw.csv"))
     ix = {h: i for i, h in enumerate(hdr)}
     def to_bytes(r, key):
         u = units[ix[key]].lower(); v = num(r[ix[key]])
@@ -32,10 +33,10 @@ for w in ("C4", "C5"):
                   "source": f"ncu --set full --clock-control none --profile-from-start off python tools/prof_gl.py {w} 3 "
                             "(dram__bytes_read.sum + dram__bytes_write.sum over every kernel of the last fwd+bwd, "
                             "torch's own fill/copy kernels inside the call included)"}
-json.dump(traffic, open(os.path.join(DST, "r01_traffic.json"), "w"), indent=1)
+json.dump(traffic, open(os.path.join(DST, f"{R}_traffic.json"), "w"), indent=1)
 
 for f in os.listdir(SRC):
-    if f.startswith("r01_") and (f.endswith(".json") or f.endswith(".csv") or f.endswith(".txt")):
+    if f.startswith(R + "_") and (f.endswith(".json") or f.endswith(".csv") or f.endswith(".txt")):
         shutil.copy(os.path.join(SRC, f), os.path.join(DST, f))
 
 def table(path, title, cols):
@@ -60,6 +61,7 @@ def table(path, title, cols):
 COLS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        ("lts__t_sectors.sum", "L2 sectors"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
         ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1 %"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
         ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe %"),
@@ -68,7 +70,7 @@ COLS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
         ("launch__registers_per_thread", "regs"), ("smsp__inst_executed.sum", "warp inst"), ("launch__grid_size", "grid")]
 
 # launch list of the bench command
-rows = list(csv.reader(open(os.path.join(SRC, "r01_launches_C5.csv"))))
+rows = list(csv.reader(open(os.path.join(SRC, f"{R}_launches_C5.csv"))))
 start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 hdr = rows[start]; ix = {h: i for i, h in enumerate(hdr)}
 agg = collections.defaultdict(lambda: [0, 0.0])
@@ -79,7 +81,7 @@ for r in rows[start + 1:]:
     a = agg[short(r[ix["Kernel Name"]])]; a[0] += 1; a[1] += v
 tot_ours = sum(v for k, (c, v) in agg.items() if k.startswith("k_"))
 tot_all = sum(v for c, v in agg.values())
-bench = json.loads(open(os.path.join(SRC, "r01_bench_C5.json")).read())
+bench = json.loads(open(os.path.join(SRC, f"{R}_bench_C5.json")).read())
 live = bench["kernels_ms_per_step"]; live_tot = sum(live.values())
 def live_share(name):
     base = re.sub(r"<.*", "", name)
@@ -89,16 +91,16 @@ for k, (c, v) in agg.items():
     if k.startswith("k_"):
         f = re.sub(r"<.*", "", k); f = "k_bwd3" if f == "k_bwd3_mma" else f
         fam[f][0] += c; fam[f][1] += v
-md = ["# profiles/r01 — ncu evidence, round 1 (B200, sm_100a, 1965 MHz, no clock control)\n",
+md = [f"# profiles/{R} — ncu evidence (B200, sm_100a, 1965 MHz, no clock control)\n",
       "All captures ran under `gpurun` on one GPU, each only after the same command had exited 0 without ncu "
       "(`tools/gpu_profiles_final.sh`).\n",
       "## 1. Launch list of the bench command (cold-cache, serialised: compare SHARES)\n",
-      "```\nncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file r01_launches_C5.csv \\\n"
+      f"```\nncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file {R}_launches_C5.csv \\\n"
       "    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras\n```\n",
       f"{sum(c for c, v in agg.values())} launches, {tot_all / 1e3:.1f} ms under ncu; our kernels {tot_ours / 1e3:.1f} ms "
       f"({100 * tot_ours / tot_all:.1f} %), the rest is torch (L2-flush fill, pinned-copy, MSE, fused Adam, zero_grad).  "
       "Share = of our kernels' time; `live` = the same share from `kernels_ms_per_step` of the bench line "
-      "(`r01_bench_C5.json`, CUDA events, warm caches).\n",
+      f"(`{R}_bench_C5.json`, CUDA events, warm caches).\n",
       "| kernel | launches | total us (ncu) | share (ncu) | share (live) |", "|---|---|---|---|---|"]
 for k, (c, v) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
     md.append(f"| `{k}` | {c} | {v:.1f} | {100 * v / tot_ours:.1f} % | {live_share(k):.1f} % |")
@@ -107,17 +109,46 @@ md.append("The launch list contains cold graph builds (first steps without a war
           "weigh more under ncu than in the live, steady-state breakdown; everything else agrees to within a few points.\n")
 md.append("## 2. Full-set metrics (`ncu --set full --clock-control none --profile-from-start off`, one iteration inside a "
           "cudaProfilerStart/Stop range)\n")
-md.append(table(os.path.join(SRC, "r01_ncu_C5_trainstep_raw.csv"),
+md.append(table(os.path.join(SRC, f"{R}_ncu_C5_trainstep_raw.csv"),
                 "One warm train step, C5 per-GPU shard (N=16384 W=16 D=128 K=64 B=64): `python tools/prof_step.py C5 3`", COLS))
-md.append(table(os.path.join(SRC, "r01_ncu_C5_graphlayer_raw.csv"),
+md.append(table(os.path.join(SRC, f"{R}_ncu_C5_graphlayer_raw.csv"),
                 "GraphLayer fwd+bwd at the module boundary, C5: `python tools/prof_gl.py C5 3`", COLS))
-md.append(table(os.path.join(SRC, "r01_ncu_C4_graphlayer_raw.csv"),
+md.append(table(os.path.join(SRC, f"{R}_ncu_C4_graphlayer_raw.csv"),
                 "GraphLayer fwd+bwd at the module boundary, C4 (N=4096 K=32): `python tools/prof_gl.py C4 3`", COLS))
 t5, t4 = traffic["C5"], traffic["C4"]
 md.append("## 3. DRAM traffic of one GraphLayer fwd+bwd (`roofline.traffic`)\n")
 md.append(f"C5: {t5['graphlayer_fwd_bwd_dram_bytes'] / 1e6:.0f} MB over {t5['kernels']} kernels (algorithmic 1242 MB); "
           f"C4: {t4['graphlayer_fwd_bwd_dram_bytes'] / 1e6:.0f} MB over {t4['kernels']} kernels (algorithmic 309 MB).  "
-          "Per kernel in `r01_traffic.json`.\n")
-open(os.path.join(DST, "r01_ncu_C5.md"), "w").write("\n".join(md))
+          f"Per kernel in `{R}_traffic.json`.\n")
+# ---- 4. the L2 -> SM gather ceiling of the attention sweeps (what bounds GraphLayer below the HBM roofline)
+def l2_rows(path):
+    hdr, units, data = raw_rows(path)
+    ix = {h: i for i, h in enumerate(hdr)}
+    out = []
+    for r in data:
+        name = short(r[ix["Kernel Name"]])
+        if not name.startswith("k_attn_fwd") and not name.startswith("k_attn_bwd"):
+            continue
+        tu = units[ix["gpu__time_duration.sum"]]
+        t_us = num(r[ix["gpu__time_duration.sum"]]) * {"ns": 1e-3, "us": 1, "ms": 1e3, "usecond": 1, "nsecond": 1e-3, "msecond": 1e3}.get(tu, 1)
+        sect = num(r[ix["lts__t_sectors.sum"]])
+        cyc = num(r[ix["lts__cycles_elapsed.avg"]]) if "lts__cycles_elapsed.avg" in ix else float("nan")
+        out.append((name, t_us, sect, sect * 32 / (t_us * 1e-6) / 1e12, sect * 32 / cyc if cyc == cyc and cyc > 0 else float("nan"),
+                    num(r[ix["l1tex__t_sector_hit_rate.pct"]])))
+    return out
+md.append("## 4. L2 -> SM gather volume of the attention sweeps (`lts__t_sectors.sum` x 32 B)\n")
+md.append("Every target gathers its K+1 neighbour rows (W floats per window) out of L2: E*W*4 bytes per sweep, 3.5-7x the "
+          "compulsory HBM bytes of the whole layer, with an L1 hit rate of a few per cent (random top-k graph: neighbour lists "
+          "of nearby targets overlap by 4 of 64).  The sweeps run at the L2 slices' throughput "
+          "(/opt/skills/guides/B300_MICROARCH.md: ~6300 B/cycle full chip), which is what caps GraphLayer below its HBM roofline.\n")
+md.append("| config | kernel | time [us] | L2 sectors | L2 -> SM TB/s | B / L2 cycle | L1 hit % |\n|---|---|---|---|---|---|---|")
+for w in ("C5", "C4"):
+    for name, t_us, sect, tbs, bpc, l1 in l2_rows(os.path.join(SRC, f"{R}_ncu_{w}_graphlayer_raw.csv")):
+        md.append(f"| {w} | `{name}` | {t_us:.1f} | {sect:.3e} | {tbs:.2f} | {bpc:.0f} | {l1:.1f} |")
+md.append("")
+sc_path = os.path.join(SRC, f"{R}_ncu_score_raw.csv")
+if os.path.exists(sc_path):
+    md.append(table(sc_path, "Scoring, T=4096 ticks x N=16384 sensors: `python tools/score_time.py 4096 16384`", COLS))
+open(os.path.join(DST, f"{R}_ncu_C5.md"), "w").write("\n".join(md))
 print("traffic C5 %.0f MB, C4 %.0f MB" % (t5['graphlayer_fwd_bwd_dram_bytes'] / 1e6, t4['graphlayer_fwd_bwd_dram_bytes'] / 1e6))
 print("\n".join(md[:40]))
