@@ -422,8 +422,7 @@ def run_ours(args):
         raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one process per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    host_threads = max(1, (os.cpu_count() or 1) // max(world, 1))        # torchrun pins OMP_NUM_THREADS=1 per rank
-    torch.set_num_threads(host_threads)
+    host_threads = max(1, min(8, (os.cpu_count() or 1) // max(world, 1)))   # staging threads of the e2e feed, per rank
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)

@@ -65,12 +65,12 @@ class Prefetcher:
         # datasets/TimeDataset.py:64-73) and the H2D copy of the NEXT batches run on a worker thread, so they overlap
         # the consumer's device work even when the consumer blocks on `loss.item()` every step
         self.threaded = bool(threaded)
-        # stage_threads > 1: make sure torch's intra-op pool (which splits the staging copy and its dtype cast) has at
-        # least that many threads -- torch.distributed.run pins OMP_NUM_THREADS=1 per rank, which would leave a single
-        # thread to convert ~140 MB per step at the largest config
+        # stage_threads > 1: a large staging copy (with its dtype cast) is split by rows over that many plain host
+        # threads, each running its slice single-threaded -- independent of OMP_NUM_THREADS (torch.distributed.run
+        # pins it to 1 per rank, which would leave one thread to convert ~140 MB per step at the largest config) and
+        # without an OpenMP team whose idle workers spin on the cores the launching thread needs
         self.stage_threads = max(1, int(stage_threads))
-        if self.stage_threads > torch.get_num_threads():
-            torch.set_num_threads(self.stage_threads)
+        self._pool = None
         self.stream = torch.cuda.Stream(device=self.device)
         self._pinned = {}
         self._devbuf = {}
@@ -99,8 +99,21 @@ class Prefetcher:
             ev = self._copied.get(slot)
             if ev is not None:
                 ev.synchronize()
-        buf.copy_(t)                                # converts while copying; split over torch's intra-op threads
+        self._host_copy(buf, t)                     # converts while copying
         return buf
+
+    def _host_copy(self, dst, src):
+        n = src.shape[0] if src.dim() > 0 else 0
+        k = min(self.stage_threads, n)
+        if k <= 1 or src.numel() < (1 << 20):
+            dst.copy_(src)
+            return
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=self.stage_threads, thread_name_prefix="gdn-stage",
+                                            initializer=torch.set_num_threads, initargs=(1,))   # per-thread OpenMP setting
+        bounds = [n * i // k for i in range(k + 1)]
+        list(self._pool.map(lambda i: dst[bounds[i]:bounds[i + 1]].copy_(src[bounds[i]:bounds[i + 1]]), range(k)))
 
     def _to_device(self, slot, pos, h):
         if h.is_cuda:

@@ -93,7 +93,7 @@ for k, (c, v) in agg.items():
         fam[f][0] += c; fam[f][1] += v
 md = [f"# profiles/{R} — ncu evidence (B200, sm_100a, 1965 MHz, no clock control)\n",
       "All captures ran under `gpurun` on one GPU, each only after the same command had exited 0 without ncu "
-      "(`tools/gpu_profiles_final.sh`).\n",
+      "(`tools/gpu_profiles_r02.sh`).\n",
       "## 1. Launch list of the bench command (cold-cache, serialised: compare SHARES)\n",
       f"```\nncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file {R}_launches_C5.csv \\\n"
       "    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras\n```\n",
