@@ -632,7 +632,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(name, wl, world),
+        "config": config_dict(name, wl, world, {"parallelism": "single GPU" if world == 1 else (
+            f"window-sharded dp{world}: one int32 all-gather of the neighbour table + "
+            + ("gdn_nvls_adam (gradient all-reduce + Adam + parameter broadcast in one NVSwitch-multicast kernel)"
+               if trainer.nvls is not None else "NCCL all-reduce of the flat fp32 gradient buffer + gdn_adam_flat"))}),
         "e2e": e2e, "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,
         "step_mode": "one CUDA graph per batch shape, replayed (WindowShardedTrainer, captured after two eager steps)" if graphed

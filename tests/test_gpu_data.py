@@ -130,3 +130,69 @@ def test_test_loop_matches_reference():
     assert np.array_equal(s_dev, s_ref) and np.array_equal(s_dev, n_dev)
     with pytest.raises(RuntimeError, match="no batch"):
         test(model, [])
+
+
+def test_reference_call_sequence_end_to_end():
+    """The call sequence of main.py / train.py / test.py on top of the mirrors, on a B200: a torch DataLoader over the
+    reference-style dataset items (pageable float64, main.py:84-85) feeding train.py:63-77's step verbatim, then
+    test.py's loop, evaluate.py's scores and the summary metrics (main.py:150-174).  Checks the plumbing, not
+    accuracy: losses fall, every stage returns finite values of the reference's shapes and types."""
+    import torch.nn.functional as F
+    from torch.utils.data import DataLoader, Dataset
+    from gdn_b200 import evaluate as ev
+    from gdn_b200.data import Prefetcher
+    from gdn_b200.models.GDN import GDN
+    from gdn_b200.test import test as gdn_test
+    rng = np.random.default_rng(1)
+    N, T, W, K, D = 27, 700, 5, 5, 64
+    t = np.arange(T)
+    series = np.clip(0.5 + 0.3 * np.sin(t[None, :] * rng.uniform(0.02, 0.2, (N, 1)) + rng.uniform(0, 6, (N, 1)))
+                     + rng.normal(0, 0.02, (N, T)), 0, 1)
+    labels = np.zeros(T)
+    labels[500:560] = 1
+    series[3, 500:560] += 0.6                                           # an attack on one sensor
+    fc = torch.tensor([[j for i in range(N) for j in range(N) if i != j],
+                       [i for i in range(N) for j in range(N) if i != j]], dtype=torch.long)   # util/net_struct.py
+
+    class Windows(Dataset):                                             # datasets/TimeDataset.py:33-73 item protocol
+        def __init__(self, lo, hi, stride):
+            self.ends = list(range(max(lo, W), hi, stride))
+
+        def __len__(self):
+            return len(self.ends)
+
+        def __getitem__(self, k):
+            e = self.ends[k]
+            return (torch.from_numpy(series[:, e - W:e]).double(), torch.from_numpy(series[:, e]).double(),
+                    torch.tensor(labels[e]).double(), fc.long())
+
+    train_loader = DataLoader(Windows(0, 450, 1), batch_size=32, shuffle=True)
+    test_loader = DataLoader(Windows(450, T, 1), batch_size=32, shuffle=False)
+    device = torch.device("cuda")
+    torch.manual_seed(5)
+    model = GDN([fc], N, dim=D, input_dim=W, out_layer_num=1, out_layer_inter_dim=128, topk=K).to(device)
+    optimizer = torch.optim.Adam(model.parameters(), lr=0.001, weight_decay=0)
+    epoch_losses = []
+    for i_epoch in range(3):
+        acu_loss = 0.0
+        model.train()
+        for x, lab, attack_labels, edge_index in train_loader:          # train.py:63-77
+            x, lab, edge_index = [item.float().to(device) for item in [x, lab, edge_index]]
+            optimizer.zero_grad()
+            out = model(x, edge_index).float().to(device)
+            loss = F.mse_loss(out, lab, reduction="mean")
+            loss.backward()
+            optimizer.step()
+            acu_loss += loss.item()
+        epoch_losses.append(acu_loss / len(train_loader))
+    assert epoch_losses[-1] < epoch_losses[0] and np.isfinite(epoch_losses).all()
+    assert tuple(model.learned_graph.shape) == (N, K) and model.learned_graph.dtype == torch.int64
+    avg_loss, result = gdn_test(model, Prefetcher(test_loader, device))          # test.py:21-79 (batches prefetched)
+    assert np.isfinite(avg_loss) and len(result) == 3 and tuple(result[0].shape) == (len(test_loader.dataset), N)
+    scores, normals = ev.get_full_err_scores(result, result)                      # main.py:150-158
+    assert scores.shape == (N, len(test_loader.dataset)) and scores.dtype == np.float64 and np.isfinite(scores).all()
+    gt_labels = np.asarray(result[2])[:, 0].tolist()
+    info = ev.get_best_performance_data(scores, gt_labels, topk=1)                # main.py:164-174
+    assert len(info) == 5 and 0.0 <= info[0] <= 1.0 and all(np.isfinite(v) for v in info[:4])
+    top_sensor = int(np.argmax(scores[:, 55:100].max(axis=1)))                    # the attacked sensor stands out
+    assert top_sensor == 3
