@@ -57,6 +57,30 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
     else atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
+// (x - med) / den for one sensor's ticks: den is fixed per sensor, so the division becomes a multiplication by the
+// correctly rounded reciprocal y = RN(1/den) plus one exact-residual correction (Markstein): q0 = RN(x y),
+// r = x - den q0 (exact in one FMA), q = RN(q0 + r y) == RN(x / den) bit for bit (checked against exact rational
+// arithmetic on 5e5 cases incl. all-ones / power-of-two significands; tests/ compare the scores bit-exactly).  Outside
+// a safe exponent window (no overflow / underflow in the intermediate steps) the IEEE division runs.
+struct ExactDiv {
+    double den, y;
+    bool fast;
+    __device__ __forceinline__ void init(double d) {
+        den = d;
+        y = 1.0 / d;
+        fast = d > 0x1p-400 && d < 0x1p400;
+    }
+    __device__ __forceinline__ double operator()(double x) const {
+        const double ax = fabs(x);
+        if (fast && (ax == 0.0 || (ax > 0x1p-400 && ax < 0x1p400))) {
+            const double q0 = __dmul_rn(x, y);
+            const double r = __fma_rn(-den, q0, x);
+            return __fma_rn(r, y, q0);
+        }
+        return x / den;
+    }
+};
+
 extern __shared__ __align__(16) unsigned char score_smem[];
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -255,7 +279,7 @@ __device__ __forceinline__ void select_stats(SelectShared& S, int T, double* __r
 // atomics (8-bit digits), 2 warp ballots (5-bit digits: lane l counts bin l of every live group in registers, no
 // atomics or matches in the sweep)
 template <int EPT, int HM>
-__global__ void __launch_bounds__(256, EPT <= 16 ? 3 : 1)
+__global__ void __launch_bounds__(256, EPT <= 8 ? 4 : (EPT == 16 ? 3 : 1))
 k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ stats,
                    double* __restrict__ scores, double* __restrict__ top1) {
     __shared__ SelectShared S;
@@ -304,24 +328,35 @@ k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ st
         bool lead[SC_NQ];
 #pragma unroll
         for (int q = 0; q < SC_NQ; ++q) { cnt[q] = 0u; lead[q] = S.group[q] == q; }
+        // (group, previous digit) -> group: EPT independent shared loads, no control flow in between
+        if (swept) {
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-            if (swept && tag[e] != 7) tag[e] = S.next[tag[e]][(unsigned)(key[e] >> prev_shift) & prev_mask];
-            const bool alive = tag[e] != 7;
-            if (__ballot_sync(0xffffffffu, alive) == 0u) continue;
-            if (last) {
-                if (alive && bits > 0) {
-                    const unsigned pos = atomicAdd(&S.ncand[tag[e]], 1u);
-                    if (pos < 32u) S.cand[tag[e]][pos] = key[e];
-                }
-            } else {
+            for (int e = 0; e < EPT; ++e)
+                if (tag[e] != 7) tag[e] = S.next[tag[e]][(unsigned)(key[e] >> prev_shift) & prev_mask];
+        }
+        if (last) {
+            if (bits > 0) {
+#pragma unroll
+                for (int e = 0; e < EPT; ++e)
+                    if (tag[e] != 7) {
+                        const unsigned pos = atomicAdd(&S.ncand[tag[e]], 1u);
+                        if (pos < 32u) S.cand[tag[e]][pos] = key[e];
+                    }
+            }
+        } else if (HM == 1) {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (tag[e] != 7) atomicAdd(&S.hist[tag[e]][(unsigned)(key[e] >> shift) & mask], 1u);
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const bool alive = tag[e] != 7;
+                if (__ballot_sync(0xffffffffu, alive) == 0u) continue;
                 const unsigned dig = (unsigned)(key[e] >> shift) & mask;
                 if (HM == 0) {
                     // lanes that hit the same (group, bin) add once: the first sweeps see a handful of exponents
                     const unsigned peers = __match_any_sync(0xffffffffu, alive ? ((unsigned)tag[e] << 8 | dig) : 0xffffffffu);
                     if (alive && (peers & (0u - peers)) == lanebit) atomicAdd(&S.hist[tag[e]][dig], (unsigned)__popc(peers));
-                } else if (HM == 1) {
-                    if (alive) atomicAdd(&S.hist[tag[e]][dig], 1u);
                 } else {
                     unsigned m = __ballot_sync(0xffffffffu, alive);
 #pragma unroll
@@ -347,26 +382,42 @@ k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ st
     select_finish(S, bits);
     select_stats(S, T, stats, i);
     if (scores == nullptr && top1 == nullptr) return;
-    const double med = S.frac[0], den = fabs(S.frac[1]) + 1e-2;
+    const double med = S.frac[0];
+    ExactDiv dv;
+    dv.init(fabs(S.frac[1]) + 1e-2);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         const int t = tid + 256 * e;
-        if (t < T) srow[t] = (__longlong_as_double((long long)key[e]) - med) / den;
+        if (t < T) srow[t] = dv(__longlong_as_double((long long)key[e]) - med);
     }
     __syncthreads();
+    // batches of 4 ticks per thread: the scores, then the current maxima (independent loads, all in flight), then the
+    // rare atomics -- an atomic on top1 between two loads of top1 would serialise them
+    constexpr int SB = EPT < 4 ? EPT : 4;
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int t = tid + 256 * e;
-        if (t < T) {
-            double sc = 0.0;
-            if (t >= 3) {
+    for (int e0 = 0; e0 < EPT; e0 += SB) {
+        double sc[SB], cur[SB];
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+            const int t = tid + 256 * (e0 + u);
+            sc[u] = 0.0;
+            if (t < T && t >= 3) {
                 double acc = -0.0;
 #pragma unroll
                 for (int q = 3; q >= 0; --q) acc += srow[t - q];
-                sc = acc * 0.25;                                // == acc / 4.0 (power of two)
+                sc[u] = acc * 0.25;                             // == acc / 4.0 (power of two)
             }
-            if (scores != nullptr) scores[(size_t)i * T + t] = sc;
-            if (top1 != nullptr && sc > __ldcg(top1 + t)) atomic_max_double(top1 + t, sc);
+            cur[u] = (top1 != nullptr && t < T) ? __ldcg(top1 + t) : INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+            const int t = tid + 256 * (e0 + u);
+            if (t < T && scores != nullptr) scores[(size_t)i * T + t] = sc[u];
+        }
+#pragma unroll
+        for (int u = 0; u < SB; ++u) {
+            const int t = tid + 256 * (e0 + u);
+            if (t < T && sc[u] > cur[u]) atomic_max_double(top1 + t, sc[u]);
         }
     }
 }
@@ -400,8 +451,10 @@ k_score_sensor(const double* __restrict__ dT, int T, int resident, double* __res
     select_stats(S, T, stats, i);
     if (scores == nullptr && top1 == nullptr) return;
     const double med = S.frac[0], den = fabs(S.frac[1]) + 1e-2;
+    ExactDiv dv;
+    dv.init(den);
     if (resident) {                                          // one division per tick, in place
-        for (int t = tid; t < T; t += blockDim.x) srow[t] = (srow[t] - med) / den;
+        for (int t = tid; t < T; t += blockDim.x) srow[t] = dv(srow[t] - med);
         __syncthreads();
     }
     for (int t = tid; t < T; t += blockDim.x) {
@@ -413,7 +466,7 @@ k_score_sensor(const double* __restrict__ dT, int T, int resident, double* __res
                 for (int q = 3; q >= 0; --q) acc += srow[t - q];
             } else {
 #pragma unroll
-                for (int q = 3; q >= 0; --q) acc += (row[t - q] - med) / den;
+                for (int q = 3; q >= 0; --q) acc += dv(row[t - q] - med);
             }
             sc = acc / 4.0;
         }

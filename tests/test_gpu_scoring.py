@@ -65,3 +65,23 @@ def test_scoring_is_shift_invariant_at_scale():
     assert torch.equal(a, b) and torch.equal(ta, tb)
     assert torch.equal(ta, a.max(dim=0)[0])
     assert (a[:, :3] == 0).all()
+
+
+def test_scores_bit_exact_over_a_wide_dynamic_range():
+    """The scorer divides by multiplying with the correctly rounded reciprocal plus an exact-residual correction; this
+    must equal numpy's IEEE division bit for bit -- also for errors spanning many binades, huge and tiny sensors
+    (outside the safe exponent window the kernel divides), and quantised sensors with heavy ties."""
+    from gdn_b200 import ops
+    rng = np.random.default_rng(11)
+    T, N = 3001, 12
+    gt = rng.random((T, N)).astype(np.float32)
+    err = rng.normal(0, 1, (T, N)) * np.exp(rng.uniform(-12, 2, (T, N)))
+    pred = (gt + err).astype(np.float32)
+    pred[:, 0] = gt[:, 0] + np.float32(1e30) * rng.random(T).astype(np.float32)      # huge errors
+    pred[:, 1] = gt[:, 1] * np.float32(1.0 + 1e-7)                                    # last-bit errors
+    pred[:, 2] = gt[:, 2] + np.round(rng.random(T) * 4).astype(np.float32) / 8        # 5 distinct error levels
+    gt[:, 3] *= np.float32(1e-30); pred[:, 3] = gt[:, 3] * np.float32(1.5)            # tiny sensor
+    s, top1, _ = ops.score(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda())
+    ref = so.full_err_scores(pred, gt, vectorised=True)
+    assert np.array_equal(s.cpu().numpy(), ref)
+    assert np.array_equal(top1.cpu().numpy(), ref.max(axis=0))
