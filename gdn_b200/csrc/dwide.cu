@@ -518,7 +518,7 @@ struct LinBwdMma {
 template <int DPL, int WP>
 __global__ void __launch_bounds__(256, 2)
 k_lin_bwd_mma(const float* __restrict__ gout, const float* __restrict__ A, const float* __restrict__ Wl,
-              long long n, int W, int D, float* __restrict__ gA, double* __restrict__ part) {
+              long long n, int W, int D, float* __restrict__ gA, double* __restrict__ part, int flush_every) {
     using M = LinBwdMma<DPL, WP>;
     constexpr int TR = M::TR, GS = M::GS, AS = M::AS;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -586,7 +586,7 @@ k_lin_bwd_mma(const float* __restrict__ gout, const float* __restrict__ A, const
             }
         }
         M::gwl_acc(sG, sa, lane, acc2);
-        if (++since_flush == 4) {                                             // 24 chained MMAs per accumulator
+        if (++since_flush == flush_every) {                                   // 24 chained MMAs per accumulator at 4
             M::flush(acc2, sAcc, lane);
             since_flush = 0;
         }
@@ -1587,6 +1587,13 @@ static size_t dw_smem2(bool need_a, bool buf, int nv_double, bool red33) {
         KERNEL<<<GRID, 256, sm__, ST>>>(__VA_ARGS__);                                                  \
     } while (0)
 
+// GDN_MMA_FLUSH (diagnostics): tiles between two flushes of the tensor-core accumulators (default 4)
+static int mma_flush() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GDN_MMA_FLUSH"); v = e ? atoi(e) : 4; if (v < 1) v = 1; }
+    return v;
+}
+
 // GDN_NO_MMA (bit mask, diagnostics): 1 = k_lin_bwd, 2 = k_bwd3 fall back to the FMA kernels
 static int no_mma() {
     static int v = -1;
@@ -1623,7 +1630,7 @@ static int launch_lin_bwd_mma(const Shape& s, const float* gout, const float* A,
     const int grid = (int)(g < 1 ? 1 : g);
     cudaError_t e = ensure_dyn_smem(k_lin_bwd_mma<DPL, WP>, smem);
     if (e != cudaSuccess) return cuda_fail(e, "smem attribute k_lin_bwd_mma");
-    k_lin_bwd_mma<DPL, WP><<<grid, nw * 32, smem, st>>>(gout, A, p->lin_weight, s.n, s.W, s.D, gA, part);
+    k_lin_bwd_mma<DPL, WP><<<grid, nw * 32, smem, st>>>(gout, A, p->lin_weight, s.n, s.W, s.D, gA, part, mma_flush());
     GDN_CHECK_LAUNCH("k_lin_bwd");
     *nrec = grid;
     return 0;
