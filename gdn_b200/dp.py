@@ -169,7 +169,20 @@ class WindowShardedTrainer:
         self._graphs[key] = (graph, xs, ys, loss)
         self.graph_launches[key] = int(_lib.load().gdn_launch_count() - n0)    # our kernels per replay
 
+    def _graph_signature(self):
+        """Everything a captured step bakes in besides the batch shape: a change drops the graphs (they are
+        re-captured after two eager steps), e.g. a learning-rate schedule writing `trainer.flat.lr`."""
+        m, f = self.model, self.flat
+        return (f.lr, f.betas, f.eps, f.weight_decay, float(getattr(getattr(m, "dp", None), "p", 0.0)),
+                getattr(m, "topk", None), getattr(m, "use_tensor_cores", None), getattr(m, "graph_margin", None),
+                id(getattr(m, "_bn_sync", None)), id(getattr(m, "_dropout_mask", None)), id(getattr(m, "_graph_shard", None)))
+
     def _graph_step(self, x, y):
+        sig = self._graph_signature()
+        if sig != getattr(self, "_graph_sig", None):
+            self._graphs, self._seen, self.graph_launches, self._graph_sig = {}, {}, {}, sig
+        if getattr(self.model, "_dropout_mask", None) is not None:
+            return None                                       # explicit masks (tests) are per call: eager
         key = (tuple(x.shape), tuple(y.shape), x.dtype, y.dtype, str(x.device))
         entry = self._graphs.get(key)
         if entry is None:

@@ -102,11 +102,14 @@ class NvlsFlatAdam:
         self.slice = self.n_pad // self.world
         self.lo = self.rank * self.slice
         try:
-            if hasattr(symm, "enable_symm_mem_for_group"):
-                try:
-                    symm.enable_symm_mem_for_group(group.group_name)
-                except Exception:
-                    pass
+            if hasattr(symm, "enable_symm_mem_for_group"):      # needed by older torch builds, a no-op (that warns) on newer
+                import warnings
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    try:
+                        symm.enable_symm_mem_for_group(group.group_name)
+                    except Exception:
+                        pass
             self.flat = symm.empty(self.n_pad, dtype=torch.float32, device=dev)
             self.grad_buffer = symm.empty(self.n_pad, dtype=torch.float32, device=dev)
             self.h_param = symm.rendezvous(self.flat, group)

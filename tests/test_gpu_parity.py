@@ -669,3 +669,24 @@ def test_loss_reader_returns_every_loss_in_order():
             got.append(out)
     got += r.flush()
     assert got == [i * 0.5 for i in range(7)]
+
+
+def test_trainer_drops_its_cuda_graph_when_a_hyperparameter_changes():
+    """A captured step bakes the learning rate in: writing a new one (a schedule) must not be ignored."""
+    from gdn_b200.dp import WindowShardedTrainer
+    from gdn_b200.models.GDN import GDN
+    N, W, D, K, B = 51, 5, 64, 15, 16
+    torch.manual_seed(8)
+    x, y = torch.rand(B, N, W, device="cuda"), torch.rand(B, N, device="cuda")
+    m = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()
+    tr = WindowShardedTrainer(m, lr=1e-3, cuda_graph=True)
+    for _ in range(4):
+        tr.step(x, y)
+    assert tr._graphs
+    before = m.out_layer.mlp[0].weight.detach().clone()
+    tr.flat.lr = 0.0                                   # from now on nothing may move
+    for _ in range(4):
+        tr.step(x, y)
+    after_first = m.out_layer.mlp[0].weight.detach().clone()
+    assert torch.equal(before, after_first)
+    assert tr._graphs                                  # re-captured with the new value
