@@ -659,11 +659,18 @@ bool gram_tc_supported(int N, int D, int K) {
 }
 
 // column splits per row block: fill the SMs when there are few row blocks (N = 4096 -> 32 blocks x 4; a rank's
-// eighth of N = 16384 -> 16 blocks x 8); bounded by what the re-score's merge pool holds
+// eighth of N = 16384 -> 16 blocks x 8; N = 16384 on one GPU -> 128 blocks x 2); bounded by what the re-score's merge
+// pool holds
 static void tc_split(int N, int D, int K, int blocks, int* nsplit, int* tiles_per_split) {
     const int ntiles = ceil_div(N, TC_BN), L = K + TC_SLACK;
     int want = num_sms() / blocks;
-    if (want < 1) want = 1;
+    // never a single split: with two, a (row, warpgroup) segment of a warm-started sweep ends below L entries and skips
+    // its final compaction (measured at N = 16384: k_gram_tc 0.367 -> 0.26 ms, k_rescore 0.187 -> 0.21 for the two extra
+    // segments it merges)
+    if (want < 2) want = 2;
+    static int force = -1;                       // diagnostics: GDN_TC_SPLIT forces the number of column splits
+    if (force < 0) { const char* e = getenv("GDN_TC_SPLIT"); force = e ? atoi(e) : 0; }
+    if (force > 0) want = force;
     if (want > TC_MAXSPLIT) want = TC_MAXSPLIT;
     while (want > 1 && 2 * (2 * want) * L > 32 * (D + 4)) --want;
     const int tps = ceil_div(ntiles, want);
