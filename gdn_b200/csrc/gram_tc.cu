@@ -661,13 +661,13 @@ bool gram_tc_supported(int N, int D, int K) {
 // column splits per row block: fill the SMs when there are few row blocks (N = 4096 -> 32 blocks x 4; a rank's
 // eighth of N = 16384 -> 16 blocks x 8; N = 16384 on one GPU -> 128 blocks x 2); bounded by what the re-score's merge
 // pool holds
-static void tc_split(int N, int D, int K, int blocks, int* nsplit, int* tiles_per_split) {
+static void tc_split(int N, int D, int K, int blocks, bool cold, int* nsplit, int* tiles_per_split) {
     const int ntiles = ceil_div(N, TC_BN), L = K + TC_SLACK;
     int want = num_sms() / blocks;
-    // never a single split: with two, a (row, warpgroup) segment of a warm-started sweep ends below L entries and skips
-    // its final compaction (measured at N = 16384: k_gram_tc 0.367 -> 0.26 ms, k_rescore 0.187 -> 0.21 for the two extra
-    // segments it merges)
-    if (want < 2) want = 2;
+    // warm-started sweeps never run as a single split: with two, a (row, warpgroup) segment ends below L entries and
+    // skips its final compaction (measured at N = 16384: k_gram_tc 0.367 -> 0.26 ms, k_rescore 0.187 -> 0.21 for the two
+    // extra segments it merges).  A cold sweep compacts anyway and prefers the longer columns (1.53 vs 2.26 ms).
+    if (want < 2 && !cold) want = 2;
     static int force = -1;                       // diagnostics: GDN_TC_SPLIT forces the number of column splits
     if (force < 0) { const char* e = getenv("GDN_TC_SPLIT"); force = e ? atoi(e) : 0; }
     if (force > 0) want = force;
@@ -681,7 +681,7 @@ static void tc_split(int N, int D, int K, int blocks, int* nsplit, int* tiles_pe
 static size_t tc_units(int N, int D, int K) {
     int nsplit, tps;
     const int blocks = ceil_div(N, TC_BM);
-    tc_split(N, D, K, blocks, &nsplit, &tps);
+    tc_split(N, D, K, blocks, false, &nsplit, &tps);
     size_t u = (size_t)blocks * nsplit;
     const size_t floor_u = (size_t)num_sms() + TC_MAXSPLIT;           // blocks_sub * nsplit_sub <= max(num_sms, blocks_sub)
     return u > floor_u ? u : floor_u;
@@ -703,7 +703,8 @@ int launch_gram_tc(const float* V, int N, int D, int K, int row0, int row1, int6
     const int L = K + TC_SLACK, C = TC_MAXC, KB = D / TC_BK;
     const int rb0 = row0 / TC_BM, blocks = ceil_div(row1, TC_BM) - rb0;
     int nsplit, tps;
-    tc_split(N, D, K, blocks, &nsplit, &tps);
+    const bool cold = kth == nullptr || !(margin < 1e30f);          // no hints, or the caller says they are not valid yet
+    tc_split(N, D, K, blocks, cold, &nsplit, &tps);
     const int S = 2 * nsplit;
     const size_t units = tc_units(N, D, K);
     GDN_CHECK_ARG((size_t)blocks * nsplit <= units, "gram_tc: %d row blocks x %d splits exceed the workspace", blocks, nsplit);

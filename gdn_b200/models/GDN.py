@@ -152,7 +152,7 @@ class GDN(nn.Module):
         self._graph_shard = None if (rank is None or world is None or world <= 1) else (int(rank), int(world), group)
         self._graph_cache = None
 
-    def _build_graph_sharded(self, w):
+    def _build_graph_sharded(self, w, margin):
         import torch.distributed as dist
         from ..dp import graph_row_shard
         rank, world, group = self._graph_shard
@@ -160,7 +160,7 @@ class GDN(nn.Module):
         r0, r1, chunk = graph_row_shard(N, rank, world)
         nbr = torch.empty((world * chunk, K + 1), dtype=torch.int32, device=w.device)
         if r1 > r0:
-            ops.graph_build(w, K, use_tensor_cores=self.use_tensor_cores, kth=self._kth, margin=self.graph_margin,
+            ops.graph_build(w, K, use_tensor_cores=self.use_tensor_cores, kth=self._kth, margin=margin,
                             rows=(r0, r1), out=(None, nbr))
         # ONE in-place all-gather of the int32 table (4 (K+1) bytes per sensor); the int64 learned_graph the API
         # publishes is rebuilt locally from it (the table records where each row sat in its own top-k)
@@ -178,14 +178,18 @@ class GDN(nn.Module):
         if self.training or self._graph_cache is None or self._graph_cache[0] != key:
             if self._kth is None or self._kth.device != w.device or self._kth.numel() != w.shape[0]:
                 self._kth = torch.full((w.shape[0],), float("-inf"), dtype=torch.float32, device=w.device)
+                self._kth_warm = False
+            # an infinite margin tells the builder that the hints are not valid yet (cold sweep, first build)
+            margin = self.graph_margin if getattr(self, "_kth_warm", False) else float("inf")
+            self._kth_warm = True
             # warm start: last build's K-th cosine per row (the embedding moves one optimiser step between
             # builds); purely an accelerator -- stale hints are detected and recomputed exactly
             if self._graph_shard is not None and self.training:
                 # collective: every rank of the group must be in its training forward (eval builds locally)
-                idx, nbr = self._build_graph_sharded(w)
+                idx, nbr = self._build_graph_sharded(w, margin)
             else:
                 idx, nbr = ops.graph_build(w, self.topk, use_tensor_cores=self.use_tensor_cores, kth=self._kth,
-                                           margin=self.graph_margin)
+                                           margin=margin)
             self._graph_cache = None if self.training else (key, idx, nbr)
             return idx, nbr
         return self._graph_cache[1], self._graph_cache[2]

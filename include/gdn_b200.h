@@ -160,7 +160,8 @@ int    gdn_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_
  * PREVIOUS build (anything <= -2 or NaN = no hint); the tcgen05 engine admits only values above
  * kth[i] - margin, which removes almost all selection work when the embedding moved by one optimiser
  * step.  Rows whose hint turns out stale are recomputed exactly, so the result never depends on the
- * hint.  Out: this build's K-th largest cosine per row. */
+ * hint.  margin = +infinity says "kth holds no valid hints yet" (first build): a cold sweep, kth is only written.
+ * Out: this build's K-th largest cosine per row. */
 int    gdn_graph_build_warm(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr,
                             void* ws, size_t ws_bytes, int use_tensor_cores, float* kth, float margin,
                             void* stream);
