@@ -447,7 +447,7 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int row0, 
     __shared__ float s_av[RS_WARPS][RS_MAXSEL];             // approximate (tensor-core) values of the selection
     __shared__ int s_j[RS_WARPS][RS_MAXSEL];
     __shared__ int s_out[RS_WARPS][TC_MAXL];
-    extern __shared__ __align__(16) float rs_smem[];        // per warp: tile [32][D+4] (first the pool keys/idx [2][S*L]), v_i [D]
+    extern __shared__ __align__(16) float rs_smem[];        // per warp: tile [32][D/2+4] (first the pool keys/idx [2][S*L]), v_i [D]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int li = blockIdx.x * RS_WARPS + wid;               // row inside the range = row of the candidate buffers
     const int i = row0 + li;
@@ -455,7 +455,10 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int row0, 
     // a pipeline protocol error in k_gram_tc (bounded mbarrier wait expired; never observed) leaves candidate
     // lists incomplete: hand every block to the exact engine instead of trusting them
     if (*tc_err != 0 && lane == 0) block_flags[i / 64] = 1;
-    constexpr int TS = D + 4;                                    // tile row stride: conflict-free float4 row reads
+    // the candidate rows are staged HALF a row at a time (the fmaf chain simply continues): half the shared memory
+    // per warp, twice the resident warps for a kernel whose 128-step dependent chain is latency-bound
+    constexpr int DH = D / 2;
+    constexpr int TS = DH + 4;                                   // tile row stride: conflict-free float4 row reads
     float* tile = rs_smem + (size_t)wid * (32 * TS + D);
     float* svi = tile + 32 * TS;
     unsigned* pk = reinterpret_cast<unsigned*>(tile);        // the pool is dead before the tile is first written
@@ -551,36 +554,42 @@ k_rescore(const float* __restrict__ V, const float* __restrict__ nrm, int row0, 
     for (int l0 = 0; l0 < have; l0 += 32) {
         const int l = l0 + lane;
         const int j = l < have ? s_j[wid][l] : -1;
-        // stage the 32 candidate rows with coalesced 16-byte loads, 8 loads in flight per lane
-        constexpr int LPR = D / 4, RPP = 32 / LPR;            // lanes per row, rows per warp-wide load
+        // stage the 32 candidate half-rows with coalesced 16-byte loads, 8 loads in flight per lane
+        constexpr int LPR = DH / 4, RPP = 32 / LPR;           // lanes per half-row, rows per warp-wide load
         const int sub = lane / LPR, dq = 4 * (lane % LPR);
+        float dot = 0.f;
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 8 * RPP) {
-            float4 r[8];
+            for (int c0 = 0; c0 < 32; c0 += 8 * RPP) {
+                float4 r[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int jc = __shfl_sync(0xffffffffu, j, c0 + u * RPP + sub);
-                r[u] = jc >= 0 ? __ldg(reinterpret_cast<const float4*>(V + (size_t)jc * D + dq))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 8; ++u) {
+                    const int jc = __shfl_sync(0xffffffffu, j, c0 + u * RPP + sub);
+                    r[u] = jc >= 0 ? __ldg(reinterpret_cast<const float4*>(V + (size_t)jc * D + hf * DH + dq))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    *reinterpret_cast<float4*>(tile + (c0 + u * RPP + sub) * TS + dq) = r[u];
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                *reinterpret_cast<float4*>(tile + (c0 + u * RPP + sub) * TS + dq) = r[u];
-        }
-        __syncwarp();
-        if (j >= 0) {
-            // one fmaf chain over d = 0..D-1, exactly as graph_build.cu accumulates it
-            const float4* vj4 = reinterpret_cast<const float4*>(tile + lane * TS);
-            const float4* vi4 = reinterpret_cast<const float4*>(svi);
-            float dot = 0.f;
+            __syncwarp();
+            if (j >= 0) {
+                // one fmaf chain over d = 0..D-1, exactly as graph_build.cu accumulates it
+                const float4* vj4 = reinterpret_cast<const float4*>(tile + lane * TS);
+                const float4* vi4 = reinterpret_cast<const float4*>(svi + hf * DH);
 #pragma unroll 8
-            for (int q = 0; q < D / 4; ++q) {
-                const float4 a = vi4[q], b = vj4[q];
-                dot = fmaf(a.x, b.x, dot);
-                dot = fmaf(a.y, b.y, dot);
-                dot = fmaf(a.z, b.z, dot);
-                dot = fmaf(a.w, b.w, dot);
+                for (int q = 0; q < DH / 4; ++q) {
+                    const float4 a = vi4[q], b = vj4[q];
+                    dot = fmaf(a.x, b.x, dot);
+                    dot = fmaf(a.y, b.y, dot);
+                    dot = fmaf(a.z, b.z, dot);
+                    dot = fmaf(a.w, b.w, dot);
+                }
             }
+            __syncwarp();
+        }
+        if (j >= 0) {
             const float c = dot / (ni * nrm[j]);
             // ranking key: exact cosine descending, then index ascending
             s_key[wid][l] = ((unsigned long long)f2key(c) << 32) | (unsigned long long)(0xffffffffu - (unsigned)j);
@@ -672,7 +681,7 @@ static void tc_split(int N, int D, int K, int blocks, bool cold, int* nsplit, in
     if (force < 0) { const char* e = getenv("GDN_TC_SPLIT"); force = e ? atoi(e) : 0; }
     if (force > 0) want = force;
     if (want > TC_MAXSPLIT) want = TC_MAXSPLIT;
-    while (want > 1 && 2 * (2 * want) * L > 32 * (D + 4)) --want;
+    while (want > 1 && 2 * (2 * want) * L > 32 * (D / 2 + 4)) --want;
     const int tps = ceil_div(ntiles, want);
     *tiles_per_split = tps;
     *nsplit = ceil_div(ntiles, tps);
@@ -749,8 +758,8 @@ int launch_gram_tc(const float* V, int N, int D, int K, int row0, int row1, int6
     k_gram_tc<<<dim3(blocks, nsplit), TC_THREADS, smem, st>>>(tm_hi, tm_lo, N, KB, L, C, tps, rb0, bufv, bufj, rowcnt, kth,
                                                               margin, err, dbg);
     GDN_CHECK_LAUNCH("k_gram_tc");
-    GDN_CHECK_ARG(2 * S * L <= 32 * (D + 4), "gram_tc: candidate pool (%d) exceeds the re-score tile", 2 * S * L);
-    const size_t rs_smem = (size_t)RS_WARPS * (32 * (D + 4) + D) * sizeof(float);
+    GDN_CHECK_ARG(2 * S * L <= 32 * (D / 2 + 4), "gram_tc: candidate pool (%d) exceeds the re-score tile", 2 * S * L);
+    const size_t rs_smem = (size_t)RS_WARPS * (32 * (D / 2 + 4) + D) * sizeof(float);
     auto rescore = D == 128 ? k_rescore<128> : k_rescore<64>;
     e = ensure_dyn_smem_ptr(reinterpret_cast<const void*>(rescore), rs_smem);
     if (e != cudaSuccess) return cuda_fail(e, "smem attr k_rescore");
