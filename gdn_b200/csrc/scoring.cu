@@ -100,7 +100,7 @@ struct SelectShared {
     unsigned ncand[SC_NQ];
     int group[SC_NQ];                      // first rank with the same prefix (shares its histogram / candidates)
     unsigned char next[SC_NQ][256];        // (group, digit) of the last sweep -> group after it, 7 = no rank left there
-    unsigned long long wmin[8], wmax[8];
+    unsigned long long wmin[16], wmax[16];
     double frac[2];
 };
 
@@ -114,7 +114,7 @@ __device__ __forceinline__ void select_init(SelectShared& S, int T, unsigned lon
     }
     if (lane == 0) { S.wmin[wid] = kmin; S.wmax[wid] = kmax; }
     __syncthreads();
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
         kmin = S.wmin[w] < kmin ? S.wmin[w] : kmin;
         kmax = S.wmax[w] > kmax ? S.wmax[w] : kmax;
     }
@@ -278,8 +278,8 @@ __device__ __forceinline__ void select_stats(SelectShared& S, int T, double* __r
 // HM = how a counting sweep builds its histograms: 0 match-aggregated shared atomics (8-bit digits), 1 plain shared
 // atomics (8-bit digits), 2 warp ballots (5-bit digits: lane l counts bin l of every live group in registers, no
 // atomics or matches in the sweep)
-template <int EPT, int HM>
-__global__ void __launch_bounds__(256, EPT <= 8 ? 4 : (EPT == 16 ? 3 : 1))
+template <int EPT, int HM, int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : (EPT <= 8 ? 4 : (EPT == 16 ? 3 : 1)))
 k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ stats,
                    double* __restrict__ scores, double* __restrict__ top1) {
     __shared__ SelectShared S;
@@ -291,7 +291,7 @@ k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ st
 #pragma unroll
     for (int j = 0; j < 5; ++j) inv[j] = ((lane >> j) & 1) ? 0u : 0xffffffffu;
     const double* row = dT + (size_t)i * T;
-    double* srow = reinterpret_cast<double*>(score_smem);      // [256 * EPT]
+    double* srow = reinterpret_cast<double*>(score_smem);      // [NT * EPT]
     unsigned long long key[EPT];
     unsigned char tag[EPT];                                    // group of the element (a rank id), 7 = out of the race
     // min / max of the keys word by word (integer min/max are one instruction; a double compare-select is a dozen):
@@ -299,7 +299,7 @@ k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ st
     unsigned hmin = 0xffffffffu, hmax = 0u, lmin = 0xffffffffu, lmax = 0u;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-        const int t = tid + 256 * e;
+        const int t = tid + NT * e;
         key[e] = t < T ? (unsigned long long)__double_as_longlong(row[t]) : 0ull;
         tag[e] = t < T ? 0 : 7;
         if (t < T) {
@@ -387,7 +387,7 @@ k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ st
     dv.init(fabs(S.frac[1]) + 1e-2);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-        const int t = tid + 256 * e;
+        const int t = tid + NT * e;
         if (t < T) srow[t] = dv(__longlong_as_double((long long)key[e]) - med);
     }
     __syncthreads();
@@ -399,7 +399,7 @@ k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ st
         double sc[SB], cur[SB];
 #pragma unroll
         for (int u = 0; u < SB; ++u) {
-            const int t = tid + 256 * (e0 + u);
+            const int t = tid + NT * (e0 + u);
             sc[u] = 0.0;
             if (t < T && t >= 3) {
                 double acc = -0.0;
@@ -411,12 +411,12 @@ k_score_sensor_reg(const double* __restrict__ dT, int T, double* __restrict__ st
         }
 #pragma unroll
         for (int u = 0; u < SB; ++u) {
-            const int t = tid + 256 * (e0 + u);
+            const int t = tid + NT * (e0 + u);
             if (t < T && scores != nullptr) scores[(size_t)i * T + t] = sc[u];
         }
 #pragma unroll
         for (int u = 0; u < SB; ++u) {
-            const int t = tid + 256 * (e0 + u);
+            const int t = tid + NT * (e0 + u);
             if (t < T && sc[u] > cur[u]) atomic_max_double(top1 + t, sc[u]);
         }
     }
@@ -489,23 +489,26 @@ int launch_score(const float* pred, const float* gt, int T, int N, double* score
     GDN_CHECK_LAUNCH("k_delta_transpose");
     static int hm = -1;                                     // diagnostics: GDN_SCORE_HM = 0 | 1 | 2 (see k_score_sensor_reg)
     if (hm < 0) { const char* e = getenv("GDN_SCORE_HM"); hm = e ? atoi(e) : 1; }
-#define SC_LAUNCH_REG2(EPTV, HMV)                                                                      \
+#define SC_LAUNCH_REG3(EPTV, HMV, NTV)                                                                 \
     do {                                                                                              \
-        const size_t sm__ = (size_t)256 * (EPTV) * sizeof(double);                                    \
-        cudaError_t e__ = ensure_dyn_smem(k_score_sensor_reg<EPTV, HMV>, sm__);                       \
+        const size_t sm__ = (size_t)(NTV) * (EPTV) * sizeof(double);                                  \
+        cudaError_t e__ = ensure_dyn_smem(k_score_sensor_reg<EPTV, HMV, NTV>, sm__);                  \
         if (e__ != cudaSuccess) return cuda_fail(e__, "smem attribute k_score_sensor_reg");           \
-        k_score_sensor_reg<EPTV, HMV><<<N, 256, sm__, st>>>(dT, T, stats, scores, top1);              \
+        k_score_sensor_reg<EPTV, HMV, NTV><<<N, NTV, sm__, st>>>(dT, T, stats, scores, top1);         \
     } while (0)
+#define SC_LAUNCH_REG2(EPTV, HMV) SC_LAUNCH_REG3(EPTV, HMV, 256)
 #define SC_LAUNCH_REG(EPTV)                                                                            \
     do {                                                                                              \
         if (hm == 0) SC_LAUNCH_REG2(EPTV, 0);                                                         \
         else if (hm == 1) SC_LAUNCH_REG2(EPTV, 1);                                                    \
         else SC_LAUNCH_REG2(EPTV, 2);                                                                 \
     } while (0)
+    // 4097..8192 ticks: 512 threads x 16 ticks beats 256 x 32 (0.26 vs 0.41 ms at T = 8000, N = 4096: 122 registers
+    // leave one CTA per SM); up to 4096 ticks 256 threads win (0.45 vs 0.58 ms at T = 4096, N = 16384)
     if (T <= 256 * 4) SC_LAUNCH_REG(4);
     else if (T <= 256 * 8) SC_LAUNCH_REG(8);
     else if (T <= 256 * 16) SC_LAUNCH_REG(16);
-    else if (T <= 256 * 32) SC_LAUNCH_REG(32);
+    else if (T <= 512 * 16) SC_LAUNCH_REG3(16, 1, 512);
     else {
         const int resident = T <= SC_RESIDENT ? 1 : 0;
         const size_t smem = resident ? align_up((size_t)T * sizeof(double), 16) : 0;
@@ -515,6 +518,7 @@ int launch_score(const float* pred, const float* gt, int T, int N, double* score
     }
 #undef SC_LAUNCH_REG
 #undef SC_LAUNCH_REG2
+#undef SC_LAUNCH_REG3
     GDN_CHECK_LAUNCH("k_score_sensor");
     return 0;
 }
