@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "launchers.h"
+#include "f32x2.cuh"
 
 namespace gdn {
 
@@ -242,12 +243,12 @@ k_attn_fwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
                 }
 #pragma unroll
                 for (int j = 0; j < DP; ++j) {                   // same chain as k_lin_fwd: bit-identical rows
-                    float acc0 = 0.f, acc1 = 0.f;
+                    unsigned long long z2 = 0ull;                // (even taps, odd taps): one FFMA2 per pair
 #pragma unroll
-                    for (int w = 0; w < WP; w += 2) {
-                        acc0 = fmaf(wl[j][w], a[w], acc0);
-                        acc1 = fmaf(wl[j][w + 1], a[w + 1], acc1);
-                    }
+                    for (int w = 0; w < WP; w += 2)
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(z2) : "l"(pk2(wl[j][w], wl[j][w + 1])), "l"(pk2(a[w], a[w + 1])));
+                    float acc0, acc1;
+                    upk2(z2, acc0, acc1);
                     z[j] = (acc0 + acc1) + bs[j];
                 }
                 float* o = orow + (size_t)bb * N * (DP * 32);
