@@ -49,7 +49,7 @@ class LossReader:
 
 class Prefetcher:
     def __init__(self, batches, device, skip=(3,), dtype=torch.float32, reuse_buffers=False, threaded=False,
-                 stage_threads=1):
+                 stage_threads=1, depth=2):
         """reuse_buffers=True copies into two persistent device buffers per tensor position (no allocator
         traffic); a yielded batch is then only valid until the NEXT-BUT-ONE batch is requested -- right
         for train.py's loop, wrong for a consumer that keeps aliases of its inputs (test.py:55-57 keeps the
@@ -71,6 +71,7 @@ class Prefetcher:
         # without an OpenMP team whose idle workers spin on the cores the launching thread needs
         self.stage_threads = max(1, int(stage_threads))
         self._pool = None
+        self.depth = max(2, int(depth))      # batches in flight in the threaded mode (staging + device buffers per slot)
         self.stream = torch.cuda.Stream(device=self.device)
         self._pinned = {}
         self._devbuf = {}
@@ -148,8 +149,8 @@ class Prefetcher:
     def _iter_threaded(self):
         cur_stream = torch.cuda.current_stream(self.device)
         free_q, ready_q = queue.Queue(), queue.Queue()
-        free_q.put((0, None))
-        free_q.put((1, None))
+        for slot in range(self.depth):
+            free_q.put((slot, None))
         stop = threading.Event()
 
         def work():

@@ -27,10 +27,11 @@ def batches(n):
         yield hx[i % 4], hy[i % 4]
 
 
-def run(n, threaded, deferred, stage_threads=1):
+def run(n, threaded, deferred, stage_threads=1, depth=2):
     reader = LossReader(dev) if deferred else None
     out = []
-    for bx, by in Prefetcher(batches(n), dev, skip=(), reuse_buffers=True, threaded=threaded, stage_threads=stage_threads):
+    for bx, by in Prefetcher(batches(n), dev, skip=(), reuse_buffers=True, threaded=threaded, stage_threads=stage_threads,
+                             depth=depth):
         loss = trainer.step(bx, by)
         if deferred:
             v = reader.push(loss)
@@ -47,6 +48,12 @@ for threaded in (False, True):
         t = time.perf_counter()
         run(20, threaded, deferred)
         print(f"threaded={threaded} deferred={deferred}: {(time.perf_counter() - t) / 20 * 1e3:.2f} ms/step")
+for st in (1, 2, 4, 8):
+    for depth in (2, 3):
+        run(4, True, True, st, depth)
+        t = time.perf_counter()
+        run(20, True, True, st, depth)
+        print(f"threaded deferred stage_threads={st} depth={depth}: {(time.perf_counter() - t) / 20 * 1e3:.2f} ms/step")
 # resident batches for reference
 xd, yd = hx[0].float().to(dev), hy[0].float().to(dev)
 for _ in range(3):
