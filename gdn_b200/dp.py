@@ -242,6 +242,30 @@ def shard_loader_batches(n_batches, rank, world):
     return shard_bounds(n_batches, rank, world)
 
 
+class LoaderSlice:
+    """Batches [lo, hi) of any loader; a `gdn_b200.datasets.WindowLoader` is re-indexed instead of skipped through
+    (its batches are gathered on the device: no reason to form the ones another rank evaluates)."""
+
+    def __init__(self, inner, lo, hi):
+        self.inner, self.lo, self.hi = inner, int(lo), int(hi)
+
+    def __iter__(self):
+        inner, lo, hi = self.inner, self.lo, self.hi
+        if all(hasattr(inner, a) for a in ("dataset", "indices", "batch_size")) and not getattr(inner, "shuffle", False) \
+                and hasattr(inner.dataset, "loader"):
+            bs = inner.batch_size
+            yield from inner.dataset.loader(bs, indices=inner.indices[lo * bs:hi * bs])
+            return
+        for k, b in enumerate(inner):
+            if k >= hi:
+                break
+            if k >= lo:
+                yield b
+
+    def __len__(self):
+        return self.hi - self.lo
+
+
 def sharded_test(model, dataloader, group=None):
     """test.py:20-75 on `world` ranks ("Scoring: shards ... by window for the eval forward"): every rank runs
     the eval forward on a contiguous slice of the loader's batches.  Returns (avg_loss over ALL ticks, pred_local
@@ -250,23 +274,11 @@ def sharded_test(model, dataloader, group=None):
     from .test import test as _test
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    batches = list(range(len(dataloader)))
-    lo, hi = shard_loader_batches(len(batches), rank, world)
-
-    class _Slice:
-        def __init__(self, inner):
-            self.inner = inner
-
-        def __iter__(self):
-            for k, b in enumerate(self.inner):
-                if k >= hi:
-                    break
-                if k >= lo:
-                    yield b
+    lo, hi = shard_loader_batches(len(dataloader), rank, world)
 
     dev = next(model.parameters()).device
     if hi > lo:
-        loss, res = _test(model, _Slice(dataloader))
+        loss, res = _test(model, LoaderSlice(dataloader, lo, hi))
         pred, gt, lab = res.device_tensors
         n_batches = hi - lo
     else:                                                       # more ranks than batches

@@ -196,3 +196,34 @@ def test_reference_call_sequence_end_to_end():
     assert len(info) == 5 and 0.0 <= info[0] <= 1.0 and all(np.isfinite(v) for v in info[:4])
     top_sensor = int(np.argmax(scores[:, 55:100].max(axis=1)))                    # the attacked sensor stands out
     assert top_sensor == 3
+
+
+def test_sharded_test_slices_cover_the_run():
+    """gdn_b200.dp.sharded_test / LoaderSlice (row e-2): the per-rank slices of the evaluation loader -- the
+    device-resident WindowLoader (re-indexed) and a plain list of host batches (skipped through) -- concatenate to the
+    single-process test() result; with one process sharded_test IS test()."""
+    from gdn_b200.dp import LoaderSlice, shard_bounds, sharded_test
+    from gdn_b200.models.GDN import GDN
+    from gdn_b200.test import test as gdn_test
+    rng = np.random.default_rng(5)
+    N, T, W = 27, 300, 5
+    raw = np.concatenate([rng.random((N, T)), (rng.random((1, T)) > 0.9).astype(np.float64)], 0).tolist()
+    ds = _make("test", W, 1, raw)
+    torch.manual_seed(1)
+    model = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=64, input_dim=W, topk=5).cuda().eval()
+    loader = ds.loader(32)
+    full_loss, full = gdn_test(model, loader)
+    for world in (2, 3):
+        preds, gts, labs = [], [], []
+        for r in range(world):
+            lo, hi = shard_bounds(len(loader), r, world)
+            _, res = gdn_test(model, LoaderSlice(loader, lo, hi))
+            preds.append(res.device_tensors[0]); gts.append(res.device_tensors[1]); labs.append(res.device_tensors[2])
+        assert torch.equal(torch.cat(preds), full.device_tensors[0])
+        assert torch.equal(torch.cat(gts), full.device_tensors[1])
+        assert torch.equal(torch.cat(labs), full.device_tensors[2])
+    host = [tuple(t.cpu() if torch.is_tensor(t) else t for t in b) for b in loader]
+    _, part = gdn_test(model, LoaderSlice(host, 2, 5))
+    assert torch.equal(part.device_tensors[0], full.device_tensors[0][64:160])
+    loss1, p1, g1, l1 = sharded_test(model, loader)
+    assert abs(loss1 - full_loss) < 1e-9 and torch.equal(p1, full.device_tensors[0]) and torch.equal(l1, full.device_tensors[2][:, 0])
