@@ -169,8 +169,8 @@ WsLayout ws_layout(const Shape& s, bool fused) {
     L.part_bytes = (size_t)4 * num_sms() * rec * sizeof(double);
     L.part = take(&off, L.part_bytes);
     L.gV = take(&off, (fused && s.S > 1) ? (size_t)s.S * s.N * s.D * sizeof(float) : 0);
-    // small: c2[2D] c1[2D] part_u[sms*64] part_e[sms*2D]   (floats)
-    L.small = take(&off, ((size_t)4 * s.D + (size_t)num_sms() * (64 + 2 * s.D)) * sizeof(float));
+    // small: c2[2D] c1[2D] part_u[ctas*64] part_e[ctas*2D]   (floats; ctas = tail_max_ctas())
+    L.small = take(&off, ((size_t)4 * s.D + (size_t)tail_max_ctas() * (64 + 2 * s.D)) * sizeof(float));
     L.sums = take(&off, (size_t)2 * GDN_SUMS_MAX_DOUBLES * sizeof(double));   // local record | rank-summed copy (SyncBN)
     (void)rec;
     L.total = off;
@@ -185,7 +185,7 @@ static Small small_ptrs(const Shape& s, char* ws, const WsLayout& L) {
     float* p = (float*)(ws + L.small);
     m.c2 = p; p += 2 * s.D;
     m.c1 = p; p += 2 * s.D;
-    m.part_u = p; p += (size_t)num_sms() * 64;
+    m.part_u = p; p += (size_t)tail_max_ctas() * 64;
     m.part_e = p;
     return m;
 }

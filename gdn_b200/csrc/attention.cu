@@ -375,7 +375,7 @@ k_attn_bwd(const float* __restrict__ xT, const float* __restrict__ siT, const fl
 // Every sum runs in a fixed order (records ascending): deterministic given its inputs.
 // ---------------------------------------------------------------------------------------
 template <int WP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_attn_tail(const float* __restrict__ xT, const float* __restrict__ gsiT, const float* __restrict__ gsjT,
             const float* __restrict__ V, const float* __restrict__ Wl,
             const float* __restrict__ a_i, const float* __restrict__ a_j,
@@ -406,6 +406,15 @@ k_attn_tail(const float* __restrict__ xT, const float* __restrict__ gsiT, const 
         esi[q] = esj[q] = 0.f;
     }
     for (int i = warp; i < N; i += nwarps) {
+        // the embedding row (and the gradient row it is added to) is requested before the window sweep: the
+        // kernel is a chain of DRAM latencies at one sensor per warp, so every load of a sensor goes out together
+        float vq[8], oq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int d = lane + 32 * q;
+            vq[q] = d < D ? __ldg(V + (size_t)i * D + d) : 0.f;
+            oq[q] = (d < D && accumulate) ? gV[(size_t)i * D + d] : 0.f;
+        }
         float ssi = 0.f, ssj = 0.f;
         for (int c = 0; c < chunks; ++c) {
             const int b = c * 32 + lane;
@@ -429,14 +438,10 @@ k_attn_tail(const float* __restrict__ xT, const float* __restrict__ gsiT, const 
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int d = lane + 32 * q;
-            if (d < D) {
-                const float v = __ldg(V + (size_t)i * D + d);
-                esi[q] = fmaf(v, ssi, esi[q]);
-                esj[q] = fmaf(v, ssj, esj[q]);
-                const float add = fmaf(ssi, aei[q], ssj * aej[q]);
-                float* o = gV + (size_t)i * D + d;
-                *o = accumulate ? *o + add : add;
-            }
+            esi[q] = fmaf(vq[q], ssi, esi[q]);
+            esj[q] = fmaf(vq[q], ssj, esj[q]);
+            const float add = fmaf(ssi, aei[q], ssj * aej[q]);
+            if (d < D) gV[(size_t)i * D + d] = accumulate ? oq[q] + add : add;
         }
     }
 #pragma unroll
@@ -472,8 +477,18 @@ k_attn_tail(const float* __restrict__ xT, const float* __restrict__ gsiT, const 
         const int k = k0 + (threadIdx.x >> 4), sub = threadIdx.x & 15;
         const int e = blockIdx.x * per + k;
         double s = 0.0;
-        if (k < per && e < rec)
-            for (int q = sub; q < nrec; q += 16) s += part[(size_t)q * rec + e];
+        if (k < per && e < rec) {
+            const double* col = part + e;
+            int q = sub;
+            for (; q + 112 < nrec; q += 128) {                 // eight independent loads in flight
+                double t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = col[(size_t)(q + 16 * u) * rec];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += t[u];
+            }
+            for (; q < nrec; q += 16) s += col[(size_t)q * rec];
+        }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (sub == 0 && k < per && e < rec) sums[e] = s;
@@ -484,36 +499,66 @@ k_attn_tail(const float* __restrict__ xT, const float* __restrict__ gsiT, const 
     __syncthreads();
     if (!last) return;
     __threadfence();
-    // last CTA: the G per-CTA records of part_u [64] and part_e [2D]; thread <-> (entry, record phase), four
-    // phases per entry (eight independent loads in flight each), combined in fixed order through shared memory
+    // last CTA: the G per-CTA records of part_u [64] and part_e [2D].  thread <-> (four adjacent entries, record
+    // phase): 128-bit loads, eight in flight per thread, P = 256 / quads phases combined in fixed order through
+    // shared memory (the phase count depends on D only, so the summation order is a function of the shapes)
     const int G = gridDim.x;
-    double* sred = reinterpret_cast<double*>(&rede[0][0]);       // 4 x 512 doubles = 16 KB: rede is dead by now
+    double* sred = reinterpret_cast<double*>(&rede[0][0]);       // <= 1024 doubles = 8 KB: rede is dead by now
     __syncthreads();
-    for (int base = 0; base < 2 * D + 64; base += 64) {
-        const int e = base + (threadIdx.x & 63), ph = threadIdx.x >> 6;
-        double s = 0.0;
-        if (e < 2 * D + 64) {
-            const float* col = e < 64 ? part_u + e : part_e + (e - 64);
-            const size_t stride = e < 64 ? 64 : (size_t)2 * D;
-            double t[8];
+    if ((D & 1) == 0) {
+        const int nq = (2 * D + 64) >> 2;                        // quads: 16 of part_u, D/2 of part_e (<= 144)
+        const int P = blockDim.x / nq;
+        const int quad = threadIdx.x % nq, ph = threadIdx.x / nq;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (ph < P) {
+            const float4* col = quad < 16 ? reinterpret_cast<const float4*>(part_u) + quad
+                                          : reinterpret_cast<const float4*>(part_e) + (quad - 16);
+            const size_t stride = quad < 16 ? 16 : (size_t)(D >> 1);      // record pitch in float4
+            float4 t[8];
             int q = ph;
-            for (; q + 28 < G; q += 32) {
+            for (; q + 7 * P < G; q += 8 * P) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) t[u] = (double)__ldcg(col + (size_t)(q + 4 * u) * stride);
+                for (int u = 0; u < 8; ++u) t[u] = __ldcg(col + (size_t)(q + u * P) * stride);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) s += t[u];
+                for (int u = 0; u < 8; ++u) {
+                    s0 += (double)t[u].x; s1 += (double)t[u].y; s2 += (double)t[u].z; s3 += (double)t[u].w;
+                }
             }
-            for (; q < G; q += 4) s += (double)__ldcg(col + (size_t)q * stride);
+            for (; q < G; q += P) {
+                const float4 v = __ldcg(col + (size_t)q * stride);
+                s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+            }
+            double* o = sred + ((size_t)ph * nq + quad) * 4;
+            o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
         }
-        sred[ph * 64 + (threadIdx.x & 63)] = s;
         __syncthreads();
-        if (threadIdx.x < 64 && e < 2 * D + 64) {
-            const double tot = (sred[threadIdx.x] + sred[64 + threadIdx.x]) + (sred[128 + threadIdx.x] + sred[192 + threadIdx.x]);
+        for (int e = threadIdx.x; e < 4 * nq; e += blockDim.x) {
+            double tot = 0.0;
+            for (int h = 0; h < P; ++h) tot += sred[(size_t)h * nq * 4 + e];
             if (e < 64) gu[e] = tot;
             else if (e - 64 < D) g_aei[e - 64] = (float)tot;
             else g_aej[e - 64 - D] = (float)tot;
         }
         __syncthreads();
+    } else {                                                     // odd D: scalar loads, four phases per entry
+        for (int base = 0; base < 2 * D + 64; base += 64) {
+            const int e = base + (threadIdx.x & 63), ph = threadIdx.x >> 6;
+            double s = 0.0;
+            if (e < 2 * D + 64) {
+                const float* col = e < 64 ? part_u + e : part_e + (e - 64);
+                const size_t stride = e < 64 ? 64 : (size_t)2 * D;
+                for (int q = ph; q < G; q += 4) s += (double)__ldcg(col + (size_t)q * stride);
+            }
+            sred[ph * 64 + (threadIdx.x & 63)] = s;
+            __syncthreads();
+            if (threadIdx.x < 64 && e < 2 * D + 64) {
+                const double tot = (sred[threadIdx.x] + sred[64 + threadIdx.x]) + (sred[128 + threadIdx.x] + sred[192 + threadIdx.x]);
+                if (e < 64) gu[e] = tot;
+                else if (e - 64 < D) g_aei[e - 64] = (float)tot;
+                else g_aej[e - 64 - D] = (float)tot;
+            }
+            __syncthreads();
+        }
     }
     for (int e = threadIdx.x; e < rec; e += blockDim.x) {
         double s = __ldcg(sums + e);
@@ -658,7 +703,11 @@ int launch_attn_tail(const Shape& s, const char* ctx, const CtxLayout& L, const 
                      float* part_u, float* part_e, double* sums, unsigned int* counter, gdn_layer_grads* g,
                      cudaStream_t st) {
     const float* xT = (const float*)(ctx + L.xT);
-    const int grid = grid_for_warps(s.N, 8, num_sms());
+    // two CTAs per SM: the kernel is latency-bound.  Small sensor counts still get enough CTAs for the slice
+    // reduction of the lin-backward records (eight entries per CTA); CTAs without a sensor write zero records.
+    const int rec_ctas = (s.D * s.W + s.D + 7) / 8;
+    int grid = grid_for_warps(s.N, 8, tail_max_ctas());
+    if (grid < rec_ctas) grid = rec_ctas < tail_max_ctas() ? rec_ctas : tail_max_ctas();
 #define GDN_LAUNCH_AT(WPV)                                                                                       \
     k_attn_tail<WPV><<<grid, 256, 0, st>>>(xT, gsiT, gsjT, V, p->lin_weight, p->att_i, p->att_j, p->att_em_i,    \
                                            p->att_em_j, s.N, s.W, s.D, s.Bs, accumulate, part, nrec, part_u,     \

@@ -41,6 +41,8 @@ static inline int    ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int    round_up32(int v) { return (v + 31) & ~31; }
 
 int num_sms();
+// CTAs of k_attn_tail (its per-CTA records in the workspace are sized by this)
+inline int tail_max_ctas() { return 2 * num_sms(); }
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the request grows: keeps the call out of
 // steady-state launches (and out of CUDA-graph captures after the warm-up iterations)

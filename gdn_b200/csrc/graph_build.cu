@@ -15,6 +15,7 @@
 //     are re-scored with the same fp32 chain before ranking.
 // Also emits nbr[N][K+1]: the neighbour list GraphLayer uses after
 // remove_self_loops/add_self_loops (models/graph_layer.py:61-63).
+#include <stdlib.h>
 #include "common.cuh"
 #include "launchers.h"
 
@@ -188,6 +189,182 @@ k_gram_topk(const float* __restrict__ V, const float* __restrict__ nrm, int N, i
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Small graphs (N <= GR_MAXN; the reference's own data sets have 27..127 sensors): one WARP per row.
+// k_gram_topk gives such a graph two or three CTAs, each threading every candidate of 64 rows through a
+// serial sorted-list insert (0.33 ms at 127 sensors, 60 % of that train step).  Here a CTA owns eight rows,
+// stages 64-column slices of V in shared memory, and each warp
+//   1. computes its row's N cosines -- the same fmaf chain over d = 0..D-1 and the same acc / (n_i n_j) as the
+//      tile kernel, norms summed in k_row_norms' order, so every value is bit-identical to that engine's;
+//   2. finds the K-th largest by a 32-step bitwise search over order-preserving integer keys;
+//   3. compacts the entries above it (plus the earliest ties) and ranks them among themselves:
+//      descending value, equal values by ascending column -- the order list_insert produces.
+// dynamic smem: Bs[GR_TJ][DP] | As[GR_ROWS][D] | nb[GR_TJ] | keys[GR_ROWS][NP] | sel_key, sel_j [GR_ROWS][K]
+// ---------------------------------------------------------------------------------------
+#define GR_ROWS 8
+#define GR_TJ 64
+#define GR_MAXN 2048
+
+__device__ __forceinline__ unsigned cos_key(float v) {           // NaN -> 0 (never selected); -0 == +0
+    if (!(v == v)) return 0u;
+    const unsigned u = __float_as_uint(v + 0.f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_cos(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(GR_ROWS * 32)
+k_gram_rows(const float* __restrict__ V, int N, int D, int K, int row0, int row1,
+            int64_t* __restrict__ idx_out, int32_t* __restrict__ nbr_out, float* __restrict__ kth_out) {
+    extern __shared__ float gr_sm[];
+    const int DP = D | 1, NP = (N + 31) & ~31;
+    float* Bs = gr_sm;
+    float* As = Bs + (size_t)GR_TJ * DP;
+    float* nb = As + (size_t)GR_ROWS * D;
+    unsigned* keys = reinterpret_cast<unsigned*>(nb + GR_TJ);
+    unsigned* selk = keys + (size_t)GR_ROWS * NP;
+    int* selj = reinterpret_cast<int*>(selk + (size_t)GR_ROWS * K);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gi = row0 + blockIdx.x * GR_ROWS + wid;
+    const bool row_ok = gi < row1;
+
+    for (int e = tid; e < GR_ROWS * D; e += GR_ROWS * 32) {
+        const int r = row0 + blockIdx.x * GR_ROWS + e / D;
+        As[e] = r < row1 ? V[(size_t)r * D + e % D] : 0.f;
+    }
+    __syncthreads();
+    const float* arow = As + (size_t)wid * D;
+    float ni;
+    {
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) s = fmaf(arow[d], arow[d], s);
+        ni = sqrtf(warp_sum(s));
+    }
+    unsigned* krow = keys + (size_t)wid * NP;
+    for (int j0 = 0; j0 < N; j0 += GR_TJ) {
+        for (int e = tid; e < GR_TJ * D; e += GR_ROWS * 32) {
+            const int r = e / D, c = e % D;
+            Bs[(size_t)r * DP + c] = j0 + r < N ? V[(size_t)(j0 + r) * D + c] : 0.f;
+        }
+        __syncthreads();
+        for (int r = wid; r < GR_TJ; r += GR_ROWS) {               // the slice's norms, k_row_norms' order
+            float s = 0.f;
+            for (int d = lane; d < D; d += 32) { const float v = Bs[(size_t)r * DP + d]; s = fmaf(v, v, s); }
+            s = warp_sum(s);
+            if (lane == 0) nb[r] = sqrtf(s);
+        }
+        __syncthreads();
+        if (row_ok) {
+            const float* b0 = Bs + (size_t)lane * DP;
+            const float* b1 = Bs + (size_t)(lane + 32) * DP;
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < D; ++d) {
+                const float a = arow[d];
+                acc0 = fmaf(a, b0[d], acc0);
+                acc1 = fmaf(a, b1[d], acc1);
+            }
+            const int ja = j0 + lane, jb = j0 + lane + 32;
+            if (ja < NP) krow[ja] = ja < N ? cos_key(acc0 / (ni * nb[lane])) : 0u;
+            if (jb < NP) krow[jb] = jb < N ? cos_key(acc1 / (ni * nb[lane + 32])) : 0u;
+        }
+        __syncthreads();
+    }
+    if (!row_ok) return;
+    // ---- selection (warp-local from here on) ----
+    const int per = NP >> 5;
+    int nvalid = 0;
+    for (int q = 0; q < per; ++q) nvalid += krow[q * 32 + lane] != 0u ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+    unsigned T = 1u;                                               // fewer than K valid entries: take them all
+    int cnt = nvalid, need = 0;
+    if (nvalid >= K) {
+        T = 0u;
+        for (int bit = 31; bit >= 0; --bit) {                      // largest T with #{key >= T} >= K
+            const unsigned c = T | (1u << bit);
+            int n = 0;
+            for (int q = 0; q < per; ++q) n += krow[q * 32 + lane] >= c ? 1 : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+            if (n >= K) T = c;
+        }
+        int gt = 0;
+        for (int q = 0; q < per; ++q) gt += krow[q * 32 + lane] > T ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gt += __shfl_xor_sync(0xffffffffu, gt, o);
+        need = K - gt;                                             // ties at the threshold: the earliest columns
+        cnt = K;
+    }
+    unsigned* sk = selk + (size_t)wid * K;
+    int* sj = selj + (size_t)wid * K;
+    {
+        const unsigned lt = (1u << lane) - 1u;
+        int run = 0, eq_run = 0;
+        for (int q = 0; q < per; ++q) {
+            const unsigned k = krow[q * 32 + lane];
+            const bool eq = nvalid >= K && k == T;
+            const unsigned eqm = __ballot_sync(0xffffffffu, eq);
+            const bool take = (k > T) || (eq && eq_run + __popc(eqm & lt) < need) || (nvalid < K && k != 0u);
+            const unsigned tm = __ballot_sync(0xffffffffu, take);
+            if (take) {
+                const int pos = run + __popc(tm & lt);
+                sk[pos] = k;
+                sj[pos] = q * 32 + lane;
+            }
+            run += __popc(tm);
+            eq_run += __popc(eqm);
+        }
+    }
+    __syncwarp();
+    // rank inside the selection; a lane holds entries lane, lane + 32, ... (K <= GB_MAXK)
+    int rk[GB_MAXK / 32], rj[GB_MAXK / 32];
+    int self_pos = -1;
+#pragma unroll
+    for (int m = 0; m < GB_MAXK / 32; ++m) {
+        const int e = lane + 32 * m;
+        rk[m] = -1;
+        rj[m] = 0;
+        if (e < cnt) {
+            const unsigned k = sk[e];
+            const int j = sj[e];
+            int r = 0;
+            for (int f = 0; f < cnt; ++f) {
+                const unsigned kf = sk[f];
+                r += (kf > k || (kf == k && sj[f] < j)) ? 1 : 0;
+            }
+            rk[m] = r;
+            rj[m] = j;
+            if (j == gi) self_pos = r;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) self_pos = max(self_pos, __shfl_xor_sync(0xffffffffu, self_pos, o));
+    // k_gram_topk's conventions: idx slots past the list hold the row itself; nbr = the list without the row,
+    // then the row, then padding whose last slot records where the row sat (-2 - position)
+    const int pos = self_pos >= 0 ? self_pos : (cnt < K ? cnt : -1);
+    const int nn = cnt - (self_pos >= 0 ? 1 : 0);
+#pragma unroll
+    for (int m = 0; m < GB_MAXK / 32; ++m) {
+        if (rk[m] < 0) continue;
+        if (idx_out != nullptr) idx_out[(size_t)gi * K + rk[m]] = (int64_t)rj[m];
+        if (nbr_out != nullptr && rj[m] != gi)
+            nbr_out[(size_t)gi * (K + 1) + rk[m] - ((self_pos >= 0 && rk[m] > self_pos) ? 1 : 0)] = rj[m];
+    }
+    if (idx_out != nullptr)
+        for (int k = cnt + lane; k < K; k += 32) idx_out[(size_t)gi * K + k] = (int64_t)gi;
+    if (nbr_out != nullptr)
+        for (int o = nn + lane; o < K + 1; o += 32)
+            nbr_out[(size_t)gi * (K + 1) + o] = o == nn ? gi : ((o == K && pos >= 0) ? -2 - pos : -1);
+    if (kth_out != nullptr && lane == 0) kth_out[gi] = cnt >= K && nvalid >= K ? key_cos(T) : -INFINITY;
+}
+
+static size_t gram_rows_smem(int N, int D, int K) {
+    const size_t DP = (size_t)(D | 1), NP = (size_t)((N + 31) & ~31);
+    return (GR_TJ * DP + (size_t)GR_ROWS * D + GR_TJ + GR_ROWS * NP + 2 * (size_t)GR_ROWS * K) * sizeof(float);
+}
+
 // gram_tc.cu
 bool gram_tc_supported(int N, int D, int K);
 size_t gram_tc_ws_bytes(int N, int D, int K);
@@ -226,6 +403,16 @@ int launch_graph_build(const float* V, int N, int D, int K, int row0, int row1, 
         // exact fix-up of the (normally zero) 64-row blocks whose candidate window was ambiguous
         k_gram_topk<<<ceil_div(row1, GB_TI) - row0 / GB_TI, 256, smem, st>>>(V, nrm, N, D, K, row0 / GB_TI, idx, nbr, flags, kth);
         GDN_CHECK_LAUNCH("k_gram_topk_fixup");
+        return 0;
+    }
+    const char* rows_env = getenv("GDN_GRAM_ROWS");                  // diagnostic: 0 = always the tile kernel
+    if (N <= GR_MAXN && gram_rows_smem(N, D, K) <= 160 * 1024 && !(rows_env && rows_env[0] == '0')) {
+        // small graph: a warp per row, one launch
+        const size_t rs = gram_rows_smem(N, D, K);
+        cudaError_t e = ensure_dyn_smem(k_gram_rows, rs);
+        if (e != cudaSuccess) return cuda_fail(e, "smem attr k_gram_rows");
+        k_gram_rows<<<ceil_div(row1 - row0, GR_ROWS), GR_ROWS * 32, rs, st>>>(V, N, D, K, row0, row1, idx, nbr, kth);
+        GDN_CHECK_LAUNCH("k_gram_rows");
         return 0;
     }
     float* nrm = (float*)ws;

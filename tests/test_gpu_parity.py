@@ -326,6 +326,51 @@ def test_tensor_core_graph_engine_falls_back_on_ambiguous_rows():
     assert torch.equal(i0, i1) and torch.equal(n0, n1)
 
 
+@pytest.mark.parametrize("N,D,K", [(27, 64, 5), (51, 64, 15), (127, 128, 30), (33, 16, 33), (700, 64, 9),
+                                   (1000, 128, 100), (2048, 128, 64), (300, 100, 256)])
+def test_small_graph_kernel_is_bit_identical_to_tile_kernel(N, D, K, monkeypatch):
+    """csrc/graph_build.cu: graphs of up to 2048 sensors are built by k_gram_rows (a warp per row, threshold
+    search + ranking) -- same cosines, same order, same neighbour table and K-th cosines as the 64x64 tile
+    kernel with its sorted-list insert (GDN_GRAM_ROWS=0), including exact ties, duplicated sensors, an
+    all-zero embedding row (NaN cosines are never selected) and row-sharded builds."""
+    from gdn_b200 import ops
+    K = min(K, N)
+    torch.manual_seed(N * 7 + K)
+    V = (torch.rand(N, D, device="cuda") * 2 - 1) / D ** 0.5
+    V[3] = V[1]                                     # exact duplicates: ties broken by column order
+    V[N // 2] = V[1] * 2.0
+    V[5, : D // 2] = 0.0
+    if N > 40:
+        V[7] = 0.0                                  # zero norm: the whole row and column are NaN
+        V[N - 1] = -V[2]
+
+    def build(rows=None):
+        kth = torch.full((N,), 7.0, device="cuda")
+        out = None
+        if rows is not None:
+            out = (torch.full((N, K), -9, dtype=torch.int64, device="cuda"),
+                   torch.full((N, K + 1), -9, dtype=torch.int32, device="cuda"))
+        idx, nbr = ops.graph_build(V, K, use_tensor_cores=0, kth=kth, rows=rows, out=out)
+        torch.cuda.synchronize()
+        return idx, nbr, kth
+
+    monkeypatch.setenv("GDN_GRAM_ROWS", "0")
+    i0, n0, k0 = build()
+    monkeypatch.delenv("GDN_GRAM_ROWS")
+    i1, n1, k1 = build()
+    assert torch.equal(i0, i1) and torch.equal(n0, n1)
+    assert torch.equal(k0.view(torch.int32), k1.view(torch.int32))
+    ok = torch.ones(N, dtype=torch.bool, device="cuda")
+    if N > 40:
+        ok[7] = False                               # the all-NaN row has an empty list: nothing to rebuild from
+    assert torch.equal(ops.idx_from_nbr(n1)[ok], i1[ok])
+    if N > 256:                                     # a row range leaves the other rows alone
+        i2, n2, k2 = build(rows=(128, 256))
+        assert torch.equal(i2[128:256], i1[128:256]) and torch.equal(n2[128:256], n1[128:256])
+        assert (i2[:128] == -9).all() and (i2[256:] == -9).all() and (n2[256:] == -9).all()
+        assert torch.equal(k2[128:256], k1[128:256]) and (k2[:128] == 7.0).all()
+
+
 def test_tensor_core_engine_rejects_unsupported_shapes_loudly():
     from gdn_b200 import ops
     V = torch.rand(256, 128, device="cuda")
