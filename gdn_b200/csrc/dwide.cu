@@ -1394,8 +1394,18 @@ k_reduce_part(const T* __restrict__ part, int nrec, int rec, double* __restrict_
     __shared__ double sh[32][33];
     const int e = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0;
-    if (e < rec)
-        for (int q = threadIdx.y; q < nrec; q += 32) s += (double)part[(size_t)q * rec + e];
+    if (e < rec) {
+        const T* col = part + e;
+        int q = threadIdx.y;
+        for (; q + 224 < nrec; q += 256) {                 // eight independent loads in flight, summed in order
+            T t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = col[(size_t)(q + 32 * u) * rec];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (double)t[u];
+        }
+        for (; q < nrec; q += 32) s += (double)col[(size_t)q * rec];
+    }
     sh[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && e < rec) {

@@ -12,6 +12,7 @@ from gdn_b200.dp import WindowShardedTrainer
 from gdn_b200.models.GDN import GDN
 
 wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "C5"]
+STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 N, W, D, K, B = wl["N"], wl["W"], wl["D"], wl["K"], wl["B"]
 dev = torch.device("cuda", 0)
 torch.manual_seed(5)
@@ -46,21 +47,21 @@ for threaded in (False, True):
     for deferred in (False, True):
         run(4, threaded, deferred)
         t = time.perf_counter()
-        run(20, threaded, deferred)
-        print(f"threaded={threaded} deferred={deferred}: {(time.perf_counter() - t) / 20 * 1e3:.2f} ms/step")
+        run(STEPS, threaded, deferred)
+        print(f"threaded={threaded} deferred={deferred}: {(time.perf_counter() - t) / STEPS * 1e3:.3f} ms/step")
 for st in (1, 2, 4, 8):
     for depth in (2, 3):
         run(4, True, True, st, depth)
         t = time.perf_counter()
-        run(20, True, True, st, depth)
-        print(f"threaded deferred stage_threads={st} depth={depth}: {(time.perf_counter() - t) / 20 * 1e3:.2f} ms/step")
+        run(STEPS, True, True, st, depth)
+        print(f"threaded deferred stage_threads={st} depth={depth}: {(time.perf_counter() - t) / STEPS * 1e3:.3f} ms/step")
 # resident batches for reference
 xd, yd = hx[0].float().to(dev), hy[0].float().to(dev)
 for _ in range(3):
     trainer.step(xd, yd)
 torch.cuda.synchronize()
 t = time.perf_counter()
-for _ in range(20):
+for _ in range(STEPS):
     trainer.step(xd, yd)
 torch.cuda.synchronize()
-print(f"resident: {(time.perf_counter() - t) / 20 * 1e3:.2f} ms/step")
+print(f"resident: {(time.perf_counter() - t) / STEPS * 1e3:.3f} ms/step")
