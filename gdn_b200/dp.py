@@ -159,15 +159,30 @@ class WindowShardedTrainer:
         ops.set_dropout_counter(self._drop_counter)          # the Philox offset is read from a counter the graph bumps
         from . import _lib
         n0 = _lib.load().gdn_launch_count()
+        prev_stream = torch.cuda.current_stream(dev)
         try:
             with torch.cuda.graph(graph):
                 self._drop_counter.add_(1)
                 loss = self._flat_body(xs, ys)
+        except RuntimeError as e:
+            # A capture is refused when backward work lands on another stream -- e.g. gradient-accumulator nodes that
+            # an autograd graph created on the default stream keeps alive (a caller holding on to an output of its own
+            # forward).  The step is not lost: this trainer goes on eagerly, and says so once.
+            torch.cuda.set_stream(prev_stream)              # graph.__exit__ does not restore it when capture_end throws
+            torch.cuda.synchronize(dev)
+            self.cuda_graph = False
+            self._graphs, self.graph_launches = {}, {}
+            import warnings
+            warnings.warn("gdn_b200: CUDA-graph capture of the train step failed (%s); steps stay eager. Usual cause: "
+                          "a tensor with grad_fn from an earlier forward is still referenced." % str(e).splitlines()[0])
+            return False
         finally:
             ops.set_dropout_counter(None)
             self.model.train(was_training)
-        self._graphs[key] = (graph, xs, ys, loss)
+        # detached: the captured autograd graph (and the gradient accumulators bound to the capture stream) is released
+        self._graphs[key] = (graph, xs, ys, loss.detach())
         self.graph_launches[key] = int(_lib.load().gdn_launch_count() - n0)    # our kernels per replay
+        return True
 
     def _graph_signature(self):
         """Everything a captured step bakes in besides the batch shape: a change drops the graphs (they are
@@ -190,7 +205,8 @@ class WindowShardedTrainer:
             if seen < 2 or not self.model.training:           # lazy initialisations happen in eager steps
                 self._seen[key] = seen + 1
                 return None
-            self._capture(key, x, y)
+            if not self._capture(key, x, y):
+                return None
             entry = self._graphs[key]
         graph, xs, ys, loss = entry
         xs.copy_(x, non_blocking=True)
@@ -201,6 +217,9 @@ class WindowShardedTrainer:
         return loss
 
     def step(self, x, y):
+        """One train step (train.py:68-73); returns the loss DETACHED (train.py only reads `loss.item()`): a caller
+        that keeps the previous step's loss must not thereby keep its autograd graph -- and the gradient-accumulator
+        nodes bound to the stream it ran on -- alive into the step that is captured as a CUDA graph."""
         if self.cuda_graph and x.is_cuda and y.is_cuda and x.dtype == torch.float32 and y.dtype == torch.float32 \
                 and x.numel() <= self.GRAPH_MAX_ELEMS and x.is_contiguous() and y.is_contiguous() \
                 and not torch.cuda.is_current_stream_capturing():
@@ -213,7 +232,7 @@ class WindowShardedTrainer:
             loss = torch.nn.functional.mse_loss(out, y, reduction="mean")
             loss.backward()
             self.nvls.step()                       # all-reduce + Adam + parameter broadcast: one kernel
-            return loss
+            return loss.detach()
         if self.flat is not None:
             self.flat.zero_grad()
             out = self.model(x, None)
@@ -225,14 +244,14 @@ class WindowShardedTrainer:
                 if world > 1:
                     dist.all_reduce(self.flat.grad_buffer, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.step(grad_scale=1.0 / world)
-            return loss
+            return loss.detach()
         self.opt.zero_grad(set_to_none=True)
         out = self.model(x, None)
         loss = torch.nn.functional.mse_loss(out, y, reduction="mean")
         loss.backward()
         self.reduce()
         self.opt.step()
-        return loss
+        return loss.detach()
 
 
 # ------------------------------------------------------------------------------------------------ evaluation

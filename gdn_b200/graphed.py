@@ -49,7 +49,9 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.loss = self._body()
+            loss = self._body()
+        self.loss = loss.detach()        # static storage of the graph; the captured autograd graph itself is released
+        del loss
         ops.set_dropout_counter(None)
 
     def _body(self):

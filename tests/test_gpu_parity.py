@@ -735,3 +735,46 @@ def test_trainer_drops_its_cuda_graph_when_a_hyperparameter_changes():
     after_first = m.out_layer.mlp[0].weight.detach().clone()
     assert torch.equal(before, after_first)
     assert tr._graphs                                  # re-captured with the new value
+
+
+def test_trainer_graph_capture_with_the_previous_loss_kept_alive():
+    """`loss = trainer.step(x, y)` in a loop keeps step k's loss alive while step k+1 runs.  If that loss carried
+    its autograd graph, the gradient-accumulator nodes made on the default stream would be reused inside the
+    capture of step 3 and CUDA would refuse it (cudaErrorStreamCaptureImplicit).  step() returns detached losses."""
+    from gdn_b200.dp import WindowShardedTrainer
+    from gdn_b200.models.GDN import GDN
+    N, W, D, K, B = 27, 5, 64, 5, 32
+    torch.manual_seed(3)
+    model = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()
+    trainer = WindowShardedTrainer(model, lr=1e-3)
+    x, y = torch.rand(B, N, W, device="cuda"), torch.rand(B, N, device="cuda")
+    losses = []
+    for _ in range(8):
+        loss = trainer.step(x, y)
+        assert not loss.requires_grad
+        losses.append(loss.item())
+    assert trainer.cuda_graph and len(trainer._graphs) == 1
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+
+
+def test_trainer_goes_on_eagerly_when_the_capture_is_refused():
+    """An output of the caller's own training-mode forward, still referenced, pins accumulator nodes to the default
+    stream: the capture fails, the trainer warns once, restores the stream and keeps training eagerly."""
+    from gdn_b200.dp import WindowShardedTrainer
+    from gdn_b200.models.GDN import GDN
+    N, W, D, K, B = 27, 5, 64, 5, 32
+    torch.manual_seed(3)
+    model = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()
+    trainer = WindowShardedTrainer(model, lr=1e-3)
+    x, y = torch.rand(B, N, W, device="cuda"), torch.rand(B, N, device="cuda")
+    keep = model(x, None)                                   # holds the parameters' accumulator nodes (default stream)
+    default = torch.cuda.current_stream()
+    losses = []
+    with pytest.warns(UserWarning, match="capture of the train step failed"):
+        for _ in range(6):
+            losses.append(trainer.step(x, y).item())
+    assert keep.requires_grad
+    assert trainer.cuda_graph is False and not trainer._graphs
+    assert torch.cuda.current_stream() == default
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+    del keep
