@@ -521,13 +521,18 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    e2e_ms = e2e_timed(hx64, hy64, threaded=True, deferred=True)
+    # worker thread by batch size (Prefetcher.AUTO_THREAD_BYTES): at the reference's own data-set sizes the hand-off
+    # between two Python threads costs more than the staging it hides
+    e2e_ms = e2e_timed(hx64, hy64, threaded="auto", deferred=True)
+    feed_threaded = Prefetcher._host_bytes((hx64[0], hy64[0])) >= Prefetcher.AUTO_THREAD_BYTES
     n_losses = len(losses)
     e2e = {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": UNIT,
            "h2d_bytes_per_step": int(xs[0].numel() * 4 + ys[0].numel() * 4), "d2h_bytes_per_step": 4,
            "ms_per_step": e2e_ms / args.steps, "last_loss": losses[-1], "losses_read": n_losses,
            "host_batches": "pageable float64 [B,N,W] + [B,N] as the reference's DataLoader yields them "
-                           "(datasets/TimeDataset.py:64-73); fp32 cast + pinned staging on a worker thread inside the timed region",
+                           "(datasets/TimeDataset.py:64-73); fp32 cast + pinned staging "
+                           + ("on a worker thread" if feed_threaded else "on the calling thread (small batches)")
+                           + " inside the timed region",
            "host_bytes_staged_per_step": int(xs[0].numel() * 8 + ys[0].numel() * 8), "host_stage_threads": host_threads}
     # the round-1 variant for comparison: batches already pinned fp32, blocking loss.item() every step
     if not args.no_extras:

@@ -147,6 +147,36 @@ class WindowShardedTrainer:
         self.flat.step(grad_scale=1.0)
         return loss
 
+    def _capture_stream(self, dev):
+        if getattr(self, "_cap_stream", None) is None:
+            self._cap_stream = torch.cuda.Stream(device=dev)
+        return self._cap_stream
+
+    def _accumulators_follow(self, stream):
+        """True when the gradient accumulator of every parameter would run on `stream` if a forward were made on it now.
+        An accumulator node is created on first use and bound to the stream current at that moment; it lives as long
+        as any autograd graph references it.  One that an older graph -- an output of the caller's own forward, still
+        referenced -- keeps alive stays bound to the (default) stream of that forward, and a backward inside a capture
+        would then touch the legacy stream: CUDA refuses the capture, and a refused capture leaves torch's allocator
+        and generator state behind.  So the capture is only attempted when this probe -- a zero-gradient backward
+        through views of the parameters, with a pre-hook reading the stream each accumulator runs on -- comes back clean."""
+        params = self.flat.params
+        seen = []
+        cur = torch.cuda.current_stream(stream.device)
+        stream.wait_stream(cur)
+        with torch.cuda.stream(stream):
+            views = [p.view_as(p) for p in params]
+            hooks = [v.grad_fn.next_functions[0][0].register_prehook(
+                lambda grads: seen.append(torch.cuda.current_stream().cuda_stream)) for v in views]
+            try:
+                torch.autograd.backward(views, [torch.zeros_like(p) for p in params])
+            finally:
+                for h in hooks:
+                    h.remove()
+        cur.wait_stream(stream)
+        del views
+        return len(seen) == len(params) and all(sid == stream.cuda_stream for sid in seen)
+
     def _capture(self, key, x, y):
         from . import ops
         dev = x.device
@@ -159,30 +189,16 @@ class WindowShardedTrainer:
         ops.set_dropout_counter(self._drop_counter)          # the Philox offset is read from a counter the graph bumps
         from . import _lib
         n0 = _lib.load().gdn_launch_count()
-        prev_stream = torch.cuda.current_stream(dev)
         try:
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self._capture_stream(dev)):
                 self._drop_counter.add_(1)
                 loss = self._flat_body(xs, ys)
-        except RuntimeError as e:
-            # A capture is refused when backward work lands on another stream -- e.g. gradient-accumulator nodes that
-            # an autograd graph created on the default stream keeps alive (a caller holding on to an output of its own
-            # forward).  The step is not lost: this trainer goes on eagerly, and says so once.
-            torch.cuda.set_stream(prev_stream)              # graph.__exit__ does not restore it when capture_end throws
-            torch.cuda.synchronize(dev)
-            self.cuda_graph = False
-            self._graphs, self.graph_launches = {}, {}
-            import warnings
-            warnings.warn("gdn_b200: CUDA-graph capture of the train step failed (%s); steps stay eager. Usual cause: "
-                          "a tensor with grad_fn from an earlier forward is still referenced." % str(e).splitlines()[0])
-            return False
         finally:
             ops.set_dropout_counter(None)
             self.model.train(was_training)
         # detached: the captured autograd graph (and the gradient accumulators bound to the capture stream) is released
         self._graphs[key] = (graph, xs, ys, loss.detach())
         self.graph_launches[key] = int(_lib.load().gdn_launch_count() - n0)    # our kernels per replay
-        return True
 
     def _graph_signature(self):
         """Everything a captured step bakes in besides the batch shape: a change drops the graphs (they are
@@ -205,8 +221,17 @@ class WindowShardedTrainer:
             if seen < 2 or not self.model.training:           # lazy initialisations happen in eager steps
                 self._seen[key] = seen + 1
                 return None
-            if not self._capture(key, x, y):
+            if not self._accumulators_follow(self._capture_stream(x.device)):
+                self._blocked = getattr(self, "_blocked", 0) + 1
+                if self._blocked == 1:
+                    import warnings
+                    warnings.warn("gdn_b200: the train step is not captured as a CUDA graph while a tensor with grad_fn "
+                                  "from an earlier forward of this model is still referenced (its gradient accumulators "
+                                  "are bound to another stream); steps stay eager")
+                if self._blocked >= 8:
+                    self.cuda_graph = False                   # stop probing
                 return None
+            self._capture(key, x, y)
             entry = self._graphs[key]
         graph, xs, ys, loss = entry
         xs.copy_(x, non_blocking=True)

@@ -757,9 +757,11 @@ def test_trainer_graph_capture_with_the_previous_loss_kept_alive():
     assert all(l == l for l in losses) and losses[-1] < losses[0]
 
 
-def test_trainer_goes_on_eagerly_when_the_capture_is_refused():
-    """An output of the caller's own training-mode forward, still referenced, pins accumulator nodes to the default
-    stream: the capture fails, the trainer warns once, restores the stream and keeps training eagerly."""
+def test_trainer_defers_the_capture_while_stale_accumulators_are_alive():
+    """An output of the caller's own training-mode forward, still referenced, pins the parameters' gradient
+    accumulators to the default stream; a capture attempted now would be refused by CUDA and leave torch's generator
+    and allocator in capture state.  The trainer probes for that first: it warns once, keeps stepping eagerly (the
+    process stays healthy), and captures as soon as the reference is gone."""
     from gdn_b200.dp import WindowShardedTrainer
     from gdn_b200.models.GDN import GDN
     N, W, D, K, B = 27, 5, 64, 5, 32
@@ -767,14 +769,43 @@ def test_trainer_goes_on_eagerly_when_the_capture_is_refused():
     model = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()
     trainer = WindowShardedTrainer(model, lr=1e-3)
     x, y = torch.rand(B, N, W, device="cuda"), torch.rand(B, N, device="cuda")
-    keep = model(x, None)                                   # holds the parameters' accumulator nodes (default stream)
+    keep = model(x, None)                                   # holds the accumulator nodes (default stream)
     default = torch.cuda.current_stream()
     losses = []
-    with pytest.warns(UserWarning, match="capture of the train step failed"):
-        for _ in range(6):
+    with pytest.warns(UserWarning, match="not captured as a CUDA graph"):
+        for _ in range(5):
             losses.append(trainer.step(x, y).item())
-    assert keep.requires_grad
-    assert trainer.cuda_graph is False and not trainer._graphs
+    assert keep.requires_grad and trainer.cuda_graph and not trainer._graphs
     assert torch.cuda.current_stream() == default
-    assert all(l == l for l in losses) and losses[-1] < losses[0]
+    assert torch.rand(4, device="cuda").shape == (4,)        # generator not left in capture mode
     del keep
+    for _ in range(3):
+        losses.append(trainer.step(x, y).item())
+    assert len(trainer._graphs) == 1
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("rows,want_thread", [(8, False), (40000, True)], ids=["small-inline", "large-threaded"])
+def test_prefetcher_auto_mode_picks_the_feed_by_batch_size(rows, want_thread, monkeypatch):
+    """Prefetcher(threaded="auto"): the worker thread only when a batch carries at least AUTO_THREAD_BYTES of host
+    data; either way the batches arrive in order, cast to float32, bit-identical to a plain `.float().cuda()`."""
+    import threading
+    from gdn_b200.data import Prefetcher
+    torch.manual_seed(rows)
+    batches = [(torch.rand(rows, 32, dtype=torch.float64), torch.rand(rows, dtype=torch.float64)) for _ in range(4)]
+    assert (Prefetcher._host_bytes(batches[0]) >= Prefetcher.AUTO_THREAD_BYTES) == want_thread
+    started = []
+    real = threading.Thread.start
+
+    def spy(self):
+        if self.name == "gdn-prefetch":
+            started.append(self.name)
+        return real(self)
+
+    monkeypatch.setattr(threading.Thread, "start", spy)
+    n = 0
+    for (gx, gy), (hx, hy) in zip(Prefetcher(batches, "cuda", skip=(), threaded="auto"), batches):
+        assert gx.dtype == torch.float32 and torch.equal(gx.cpu(), hx.float()) and torch.equal(gy.cpu(), hy.float())
+        n += 1
+    assert n == 4 and bool(started) == want_thread
+    assert list(Prefetcher([], "cuda", threaded="auto")) == []
