@@ -493,7 +493,7 @@ def run_ours(args):
     def e2e_run(hxs, hys, count, threaded, deferred):
         reader = LossReader(dev) if deferred else None
         for bx, by in Prefetcher(host_batches(hxs, hys, count), dev, skip=(), reuse_buffers=True, threaded=threaded,
-                                 stage_threads=host_threads if threaded else 1):
+                                 stage_threads=host_threads):
             loss = trainer.step(bx, by)
             if deferred:
                 v = reader.push(loss)
@@ -530,7 +530,7 @@ def run_ours(args):
            "h2d_bytes_per_step": int(xs[0].numel() * 4 + ys[0].numel() * 4), "d2h_bytes_per_step": 4,
            "ms_per_step": e2e_ms / args.steps, "last_loss": losses[-1], "losses_read": n_losses,
            "host_batches": "pageable float64 [B,N,W] + [B,N] as the reference's DataLoader yields them "
-                           "(datasets/TimeDataset.py:64-73); fp32 cast + pinned staging "
+                           "(datasets/TimeDataset.py:64-73); fp32 cast + pinned staging (gdn_stage_f64_to_f32, native thread pool) "
                            + ("on a worker thread" if feed_threaded else "on the calling thread (small batches)")
                            + " inside the timed region",
            "host_bytes_staged_per_step": int(xs[0].numel() * 8 + ys[0].numel() * 8), "host_stage_threads": host_threads}
@@ -544,7 +544,7 @@ def run_ours(args):
                                                     "loss.item() sync every step"}
         ms3 = e2e_timed(hx64, hy64, threaded=False, deferred=False)
         e2e["pageable_f64_blocking_item"] = {"value": world * B * args.steps / (ms3 / 1e3), "ms_per_step": ms3 / args.steps,
-                                             "what": "pageable float64 batches staged on the calling thread, loss.item() sync every "
+                                             "what": "pageable float64 batches staged from the calling thread (gdn_stage_f64_to_f32), loss.item() sync every "
                                                      "step: train.py:63-77 unchanged around the drop-in model"}
         del hx, hy
     clocks = sampler.stop() if rank == 0 else None

@@ -52,6 +52,7 @@ SIGNATURES = {
     "gdn_version": (C.c_int, []),
     "gdn_last_error": (C.c_char_p, []),
     "gdn_launch_count": (C.c_longlong, []),
+    "gdn_stage_f64_to_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "gdn_profile_enable": (C.c_int, [C.c_int]),
     "gdn_profile_collect": (C.c_int, [C.c_char_p, C.c_size_t]),
     "gdn_graph_build_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -13,6 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgdn_b200.so")
 SOURCES = ["api.cu", "attention.cu", "dwide.cu", "graph_build.cu", "scoring.cu", "csr.cu", "windows.cu", "metrics.cu", "optim.cu"]
+HOST_SOURCES = ["host_stage.cpp"]        # host-only C++ (g++): the staging copy of the feed
+CXX = os.environ.get("CXX", "g++")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
@@ -41,6 +43,18 @@ def _compile(name, force):
     return obj, r.stderr
 
 
+def _compile_host(name, force):
+    src = os.path.join(CSRC, name)
+    obj = os.path.join(OBJ, name.replace(".cpp", ".o"))
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(src):
+        return obj, ""
+    cmd = [CXX, "-O2", "-std=c++17", "-fPIC", "-pthread", "-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"{CXX} failed for {name}:\n{r.stdout}\n{r.stderr}")
+    return obj, r.stderr
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -48,10 +62,11 @@ def build(force=False, verbose=False):
     srcs += extra
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         results = list(ex.map(lambda s: _compile(s, force), srcs))
+    results += [_compile_host(h, force) for h in HOST_SOURCES if os.path.exists(os.path.join(CSRC, h))]
     objs = [o for o, _ in results]
     relink = force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
     if relink:
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -49,7 +49,7 @@ class LossReader:
 
 class Prefetcher:
     def __init__(self, batches, device, skip=(3,), dtype=torch.float32, reuse_buffers=False, threaded=False,
-                 stage_threads=1, depth=2):
+                 stage_threads=None, depth=2):
         """reuse_buffers=True copies into two persistent device buffers per tensor position (no allocator
         traffic); a yielded batch is then only valid until the NEXT-BUT-ONE batch is requested -- right
         for train.py's loop, wrong for a consumer that keeps aliases of its inputs (test.py:55-57 keeps the
@@ -74,6 +74,13 @@ class Prefetcher:
         # threads, each running its slice single-threaded -- independent of OMP_NUM_THREADS (torch.distributed.run
         # pins it to 1 per rank, which would leave one thread to convert ~140 MB per step at the largest config) and
         # without an OpenMP team whose idle workers spin on the cores the launching thread needs
+        # float64 -> float32 (the reference's loader) goes through the library's own converter (gdn_stage_f64_to_f32:
+        # persistent native thread pool, AVX-512 + non-temporal stores, no interpreter lock); None = up to 8 threads,
+        # shared fairly between the ranks of one host; 1 = leave the copy to torch (its OpenMP team, if it has one)
+        if stage_threads is None:
+            import os
+            local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+            stage_threads = max(2, min(8, (os.cpu_count() or 2) // local))
         self.stage_threads = max(1, int(stage_threads))
         self._pool = None
         self.depth = max(2, int(depth))      # batches in flight in the threaded mode (staging + device buffers per slot)
@@ -109,6 +116,13 @@ class Prefetcher:
         return buf
 
     def _host_copy(self, dst, src):
+        if self.stage_threads > 1 and src.dtype == torch.float64 and dst.dtype == torch.float32 and not src.is_cuda \
+                and src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel():
+            from . import _lib
+            rc = _lib.load().gdn_stage_f64_to_f32(src.data_ptr(), dst.data_ptr(), src.numel(), self.stage_threads)
+            if rc != 0:
+                raise RuntimeError("gdn_stage_f64_to_f32 failed")
+            return
         n = src.shape[0] if src.dim() > 0 else 0
         k = min(self.stage_threads, n)
         if k <= 1 or src.numel() < (1 << 20):

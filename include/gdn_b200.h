@@ -134,6 +134,14 @@ const char* gdn_last_error(void);
 /* Number of kernel launches the library has enqueued so far in this process (launches recorded into a stream
  * capture count once, at capture time). */
 long long gdn_launch_count(void);
+
+/* ---- host side of the feed --------------------------------------------------------
+ * Replaces train.py:63-66 `x.float()` (one thread, an intermediate tensor) + the blocking pageable `.to(device)`:
+ * converts n doubles at `src` (pageable is fine) to floats at `dst` (normally a pinned staging buffer) in ONE pass, split
+ * over `threads` plain host threads (a persistent pool inside the library: independent of OMP_NUM_THREADS and of the
+ * caller's interpreter lock; AVX-512 convert + non-temporal stores where the CPU has them).  Host pointers, no CUDA call.
+ * Returns 0, or -1 for a NULL pointer. */
+int gdn_stage_f64_to_f32(const double* src, float* dst, size_t n, int threads);
 int gdn_profile_enable(int on);
 int gdn_profile_collect(char* buf, size_t buf_bytes);
 

@@ -28,7 +28,7 @@ def batches(n):
         yield hx[i % 4], hy[i % 4]
 
 
-def run(n, threaded, deferred, stage_threads=1, depth=2):
+def run(n, threaded, deferred, stage_threads=None, depth=2):
     reader = LossReader(dev) if deferred else None
     out = []
     for bx, by in Prefetcher(batches(n), dev, skip=(), reuse_buffers=True, threaded=threaded, stage_threads=stage_threads,
