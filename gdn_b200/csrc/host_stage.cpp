@@ -81,17 +81,21 @@ struct Pool {
         }
     }
 
-    void grow(int want) {               // under `call`
-        while ((int)workers.size() < want) {
-            const int id = (int)workers.size();
-            workers.emplace_back([this, id] { work(id); });
-            workers.back().detach();
+    void grow(int want) {               // under `call`; a host that refuses more threads just gets fewer slices
+        try {
+            while ((int)workers.size() < want) {
+                const int id = (int)workers.size();
+                workers.emplace_back([this, id] { work(id); });
+                workers.back().detach();
+            }
+        } catch (...) {
         }
     }
 
     void run(const double* s, float* d, size_t total, int threads) {
         std::lock_guard<std::mutex> g(call);
         grow(threads - 1);
+        if (threads > (int)workers.size() + 1) threads = (int)workers.size() + 1;
         {
             std::lock_guard<std::mutex> l(m);
             src = s; dst = d; n = total; parts = threads;
