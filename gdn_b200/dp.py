@@ -153,29 +153,8 @@ class WindowShardedTrainer:
         return self._cap_stream
 
     def _accumulators_follow(self, stream):
-        """True when the gradient accumulator of every parameter would run on `stream` if a forward were made on it now.
-        An accumulator node is created on first use and bound to the stream current at that moment; it lives as long
-        as any autograd graph references it.  One that an older graph -- an output of the caller's own forward, still
-        referenced -- keeps alive stays bound to the (default) stream of that forward, and a backward inside a capture
-        would then touch the legacy stream: CUDA refuses the capture, and a refused capture leaves torch's allocator
-        and generator state behind.  So the capture is only attempted when this probe -- a zero-gradient backward
-        through views of the parameters, with a pre-hook reading the stream each accumulator runs on -- comes back clean."""
-        params = self.flat.params
-        seen = []
-        cur = torch.cuda.current_stream(stream.device)
-        stream.wait_stream(cur)
-        with torch.cuda.stream(stream):
-            views = [p.view_as(p) for p in params]
-            hooks = [v.grad_fn.next_functions[0][0].register_prehook(
-                lambda grads: seen.append(torch.cuda.current_stream().cuda_stream)) for v in views]
-            try:
-                torch.autograd.backward(views, [torch.zeros_like(p) for p in params])
-            finally:
-                for h in hooks:
-                    h.remove()
-        cur.wait_stream(stream)
-        del views
-        return len(seen) == len(params) and all(sid == stream.cuda_stream for sid in seen)
+        from .graphed import accumulators_follow
+        return accumulators_follow(self.flat.params, stream)
 
     def _capture(self, key, x, y):
         from . import ops

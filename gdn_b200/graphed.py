@@ -12,6 +12,33 @@ import torch
 from gdn_b200 import ops
 
 
+def accumulators_follow(params, stream):
+    """True when the gradient accumulator of every parameter would run on `stream` if a forward were made on it now.
+    An accumulator node is created on first use and bound to the stream current at that moment; it lives as long as
+    any autograd graph references it.  One that an older graph -- the previous step's loss, an output of the caller's
+    own forward, still referenced -- keeps alive stays bound to the (default) stream of that forward, and a backward
+    inside a capture would then touch the legacy stream: CUDA refuses the capture (cudaErrorStreamCaptureImplicit),
+    and a refused capture leaves torch's allocator and generator in capture state.  So a capture is only attempted
+    when this probe -- a zero-gradient backward through views of the parameters, with a pre-hook reading the stream
+    each accumulator runs on -- comes back clean."""
+    params = [p for p in params if p.requires_grad]
+    seen = []
+    cur = torch.cuda.current_stream(stream.device)
+    stream.wait_stream(cur)
+    with torch.cuda.stream(stream):
+        views = [p.view_as(p) for p in params]
+        hooks = [v.grad_fn.next_functions[0][0].register_prehook(
+            lambda grads: seen.append(torch.cuda.current_stream().cuda_stream)) for v in views]
+        try:
+            torch.autograd.backward(views, [torch.zeros_like(p) for p in params])
+        finally:
+            for h in hooks:
+                h.remove()
+    cur.wait_stream(stream)
+    del views
+    return len(seen) == len(params) and all(sid == stream.cuda_stream for sid in seen)
+
+
 class GraphedTrainStep:
     def __init__(self, model, batch_shape, lr=1e-3, weight_decay=0.0, warmup=3):
         B, N, W = batch_shape
@@ -46,9 +73,14 @@ class GraphedTrainStep:
                     if torch.is_tensor(t):
                         t.zero_()
             self.counter.zero_()
+        if not accumulators_follow(params, side):
+            ops.set_dropout_counter(None)
+            raise RuntimeError("GraphedTrainStep: a tensor with grad_fn from an earlier forward of this model is still "
+                               "referenced (its gradient accumulators are bound to another stream); release it before "
+                               "capturing the train step")
         self.opt.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             loss = self._body()
         self.loss = loss.detach()        # static storage of the graph; the captured autograd graph itself is released
         del loss

@@ -809,3 +809,24 @@ def test_prefetcher_auto_mode_picks_the_feed_by_batch_size(rows, want_thread, mo
         n += 1
     assert n == 4 and bool(started) == want_thread
     assert list(Prefetcher([], "cuda", threaded="auto")) == []
+
+
+def test_graphed_train_step_refuses_cleanly_while_stale_accumulators_are_alive():
+    """gdn_b200.graphed.GraphedTrainStep probes before it captures: with an output of an earlier default-stream forward
+    still referenced it raises BEFORE touching a capture (torch stays usable), and builds once the reference is gone."""
+    from gdn_b200.graphed import GraphedTrainStep
+    from gdn_b200.models.GDN import GDN
+    N, W, D, K, B = 27, 5, 64, 5, 16
+    torch.manual_seed(2)
+    model = GDN([torch.zeros(2, 1, dtype=torch.long)], N, dim=D, input_dim=W, topk=K).cuda().train()
+    x, y = torch.rand(B, N, W, device="cuda"), torch.rand(B, N, device="cuda")
+    keep = model(x, None)
+    with pytest.raises(RuntimeError, match="still"):
+        GraphedTrainStep(model, (B, N, W))
+    assert torch.rand(3, device="cuda").shape == (3,) and not torch.cuda.is_current_stream_capturing()
+    del keep
+    step = GraphedTrainStep(model, (B, N, W))
+    l0 = step.step(x, y).item()
+    for _ in range(10):
+        l1 = step.step(x, y).item()
+    assert l1 < l0
