@@ -43,8 +43,12 @@ class LossReader:
         return out
 
     def flush(self):
+        """The values still in flight, oldest first; the reader is empty afterwards (ready for the next epoch)."""
         first = max(0, self.count - self.depth + 1)
-        return [self._take(k) for k in range(first, self.count)]
+        out = [self._take(k) for k in range(first, self.count)]
+        self.events = [None] * self.depth
+        self.count = 0
+        return out
 
 
 class Prefetcher:

@@ -76,7 +76,8 @@ class WindowShardedTrainer:
     """The reference's train step (train.py:68-73: zero_grad, forward, mse, backward, Adam
     step) on this rank's window shard, with the flat gradient all-reduce before the step."""
 
-    GRAPH_MAX_ELEMS = 1 << 21          # batches up to this many input values are replayed from a CUDA graph
+    # batches up to this many input values are replayed from a CUDA graph (GDN_GRAPH_MAX_ELEMS overrides)
+    GRAPH_MAX_ELEMS = int(os.environ.get("GDN_GRAPH_MAX_ELEMS", 1 << 25))
 
     def __init__(self, model, lr=1e-3, weight_decay=0.0, group=None, fused_adam=None, shard_graph=None, flat_adam=None,
                  nvls=None, cuda_graph=None, sync_bn=False):

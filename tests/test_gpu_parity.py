@@ -714,6 +714,9 @@ def test_loss_reader_returns_every_loss_in_order():
             got.append(out)
     got += r.flush()
     assert got == [i * 0.5 for i in range(7)]
+    # a second epoch through the same reader: nothing of the first one comes back
+    got2 = [o for o in (r.push(v + 10) for v in vals[:3]) if o is not None] + r.flush()
+    assert got2 == [10.0, 10.5, 11.0] and r.flush() == []
 
 
 def test_trainer_drops_its_cuda_graph_when_a_hyperparameter_changes():
