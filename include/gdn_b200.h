@@ -158,8 +158,9 @@ int gdn_profile_collect(char* buf, size_t buf_bytes);
  *          top-k entries in order, then the sensor itself, then negative padding (any negative value ends
  *          the list; when the sensor was in its own top-k the LAST slot holds -2 - its position there, the
  *          other padding slots -1, so idx is recoverable from nbr alone).
- * Either output may be NULL.  use_tensor_cores: 0 = exact fp32 CUDA-core Gram,
- * 1 = tcgen05 split-precision Gram with exact fp32 re-scoring, -1 = choose by N. */
+ * Either output may be NULL.  use_tensor_cores: 0 = exact fp32 CUDA-core Gram (a warp-per-row kernel up to
+ * 2048 sensors, a 64x64 tile kernel beyond), 1 = tcgen05 split-precision Gram with exact fp32 re-scoring
+ * (N >= 1024, dim 64 or 128, topk <= 72), -1 = choose by N.  All three produce the same bits. */
 size_t gdn_graph_build_ws_bytes(int N, int D, int K);
 int    gdn_graph_build(const float* V, int N, int D, int K, int64_t* idx, int32_t* nbr,
                        void* ws, size_t ws_bytes, int use_tensor_cores, void* stream);
