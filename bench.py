@@ -557,6 +557,11 @@ def run_ours(args):
         e2e["pinned_fp32_blocking_item"] = {"value": world * B * args.steps / (ms2 / 1e3), "ms_per_step": ms2 / args.steps,
                                             "what": "host batches pre-pinned fp32 (DataLoader(pin_memory=True) + a float32 dataset), "
                                                     "loss.item() sync every step"}
+        ms4 = e2e_timed(hx, hy, threaded="auto", deferred=True)
+        e2e["pinned_fp32_prefetched"] = {"value": world * B * args.steps / (ms4 / 1e3), "ms_per_step": ms4 / args.steps,
+                                         "what": "host batches pre-pinned fp32, the primary leg's feed (Prefetcher + LossReader: "
+                                                 "H2D on a copy stream, loss read back every step one step late): what the "
+                                                 "pipeline does when the host has no cast to do"}
         ms3 = e2e_timed(hx64, hy64, threaded=False, deferred=False)
         e2e["pageable_f64_blocking_item"] = {"value": world * B * args.steps / (ms3 / 1e3), "ms_per_step": ms3 / args.steps,
                                              "what": "pageable float64 batches staged from the calling thread (gdn_stage_f64_to_f32), loss.item() sync every "
